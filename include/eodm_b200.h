@@ -1,0 +1,154 @@
+/*
+ * eodm_b200.h -- C ABI of libeodm_b200.so: the EODM n-gram loss hot path of
+ * eastonYi/Unsupervised-ASR, hand-written for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no native plugin ABI for this path: it is a Python callable
+ * protocol over TensorFlow ops.  Each entry point below states the reference
+ * interface (file:line, relative to the reference repository) it replaces.  A
+ * TF custom op (tf_shim/eodm_tf_ops.cc), a ctypes binding (eodm_b200/_lib.py)
+ * or any other FFI binds exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 (EODM_OK) or a negative eodm_status; the message of the last
+ *     failure on the calling thread is eodm_last_error().  No C++ exception
+ *     crosses this boundary; nothing calls exit().
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host;
+ *     tensors are row-major, contiguous, fp32 unless stated.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work on
+ *     it; none synchronises the device.  All scratch memory is the caller's
+ *     (`ws`, sized by eodm_workspace_bytes); the library owns only the table.
+ *   - results are deterministic run to run: fixed-order reductions, no float
+ *     atomics.
+ *   - there is no CPU implementation behind any symbol.
+ */
+#ifndef EODM_B200_H_
+#define EODM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EODM_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum eodm_status {
+  EODM_OK = 0,
+  EODM_EINVAL = -1,       /* null pointer, bad flag, kernel column not one-hot/zero */
+  EODM_ESHAPE = -2,       /* shapes the reference itself rejects: T < kernel_size, len(py) != K */
+  EODM_ECUDA = -3,        /* a CUDA runtime call failed */
+  EODM_ENCCL = -4,        /* NCCL missing or an NCCL call failed */
+  EODM_EUNSUPPORTED = -5, /* valid input outside what the kernels cover (see message) */
+  EODM_ENOMEM = -6
+} eodm_status;
+
+/* Opaque device-resident n-gram table: the compact form of the dense one-hot
+ * Conv1D kernel that utils/tools.py:365-374 (ngram2kernel) builds. */
+typedef struct eodm_table eodm_table;
+
+int eodm_version(void);
+const char* eodm_last_error(void);
+
+/* ---- table (replaces the frozen Conv1D weights of models/EODM.py:64-70) ---- */
+
+/* From ngram2kernel's dense kernel f32[n][V][K] (host memory, C order).  Every
+ * (j, :, z) column must be one-hot or all-zero (EODM_EINVAL otherwise); zero
+ * columns may only trail the one-hot ones of an n-gram, as ngram2kernel
+ * produces them (EODM_EUNSUPPORTED otherwise).  `n` is the Conv1D kernel_size
+ * (args.data.ngram): windows are n frames long even for shorter n-grams. */
+int eodm_table_create_from_dense(const float* kernel_host, int n, int V, int K, int device, eodm_table** out);
+
+/* From compact ids int32[K][n] (host), -1 = absent (trailing only). */
+int eodm_table_create(const int32_t* ids_host, int K, int n, int V, int device, eodm_table** out);
+
+void eodm_table_destroy(eodm_table* t);
+
+/* n, V, K and the number of trie nodes of the forward traversal (any out pointer may be NULL). */
+int eodm_table_info(const eodm_table* t, int* n, int* V, int* K, int64_t* fwd_nodes, int64_t* bwd_nodes);
+
+/* Round trip for parity checks: compact ids int32[K][n] / order u8[K] (host),
+ * and the dense kernel f32[n][V][K] (host) rebuilt from the compact form. */
+int eodm_table_get_ids(const eodm_table* t, int32_t* ids_host, uint8_t* order_host);
+int eodm_table_to_dense(const eodm_table* t, float* kernel_host);
+
+/* ---- expected n-gram counts (replaces conv_op + masked reduce, models/EODM.py:14,18-20) ---- */
+
+/* Bytes of caller-owned scratch `ws` that eodm_counts_fwd/bwd need for a [B,T,V] batch. */
+size_t eodm_workspace_bytes(const eodm_table* t, int B, int T);
+
+/* S[z] = sum_{b, t <= T-n} mask[b,t] * prod_j (px[b,t+j,ids[z,j]] + 1e-15)   (f32[K])
+ * N    = sum_{b, t <  T  } mask[b,t]                                         (f32[1])
+ * px f32[B][T][V]; mask u8[B][T] (0/1, the window START is tested, EODM.py:19).
+ * EODM_ESHAPE if T < n (Conv1D 'valid' has no output). */
+int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                    float* S, float* N, void* ws, void* stream);
+
+/* dpx[b,s,v] = sum_{z,j: ids[z,j]=v} gS[z] * mask[b,s-j] * prod_{j'!=j}(px[b,s-j+j',ids[z,j']] + 1e-15)
+ * i.e. the vector-Jacobian product TF autodiff yields for the expression above
+ * (main_EODM.py:168 through EODM.py:18-20).  dpx f32[B][T][V] is overwritten. */
+int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                    const float* gS, float* dpx, void* ws, void* stream);
+
+/* loss = -sum_z py[z]*log(S[z]/N + eps);  gS[z] = dloss/dS[z]   (models/EODM.py:20-23)
+ * loss f32[1], gS f32[K] (gS may be NULL). */
+int eodm_loss_from_counts(const float* S, const float* N, const float* py, int K, float eps,
+                          float* loss, float* gS, void* stream);
+
+/* ---- the step before: tf.nn.softmax (models/EODM.py:15) and its VJP ---- */
+int eodm_softmax_fwd(const float* logits, int64_t rows, int V, float* px, void* stream);
+int eodm_softmax_bwd(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, void* stream);
+
+/* ---- materialising op: P_Ngram.__call__ (models/EODM.py:63-71) ---- */
+/* p[b,t,z] = prod_j (px[b,t+j,ids[z,j]] + 1e-15),  p f32[B][T-n+1][K]. */
+int eodm_prob_fwd(const eodm_table* t, const float* px, int B, int T, float* p, void* stream);
+/* dpx = VJP of the above for upstream dp f32[B][T-n+1][K]; dpx f32[B][T][V] overwritten. */
+int eodm_prob_bwd(const eodm_table* t, const float* px, const float* dp, int B, int T, float* dpx, void* stream);
+
+/* ---- dense bigram contraction for large vocabularies (tcgen05, 3xTF32) ---- */
+/* C[u][v] = sum_{b, t <= T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps),  C f32[V][V].
+ * V must be a multiple of 128.  ws: eodm_bigram_workspace_bytes. */
+size_t eodm_bigram_workspace_bytes(int B, int T, int V);
+int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B, int T, int V, float* C, float* N,
+                          void* ws, void* stream);
+/* dpx from upstream G f32[V][V] = dloss/dC. */
+int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B, int T, int V, const float* G, float* dpx,
+                          void* ws, void* stream);
+
+/* ---- batch sharding over the GPUs of one node (one process per GPU) ---- */
+/* In-place sum over ranks of the packed [S (K floats), N (1 float)] on `stream`
+ * (ncclAllReduce over NVLink).  `comm` is an ncclComm_t.  NCCL is resolved with
+ * dlopen at first use; EODM_ENCCL if it cannot be found. */
+int eodm_allreduce_counts(void* comm, float* S, int K, float* N, void* stream);
+/* Thin helpers so a host language without NCCL bindings can build the communicator. */
+int eodm_comm_unique_id(char id_out[128]);
+int eodm_comm_init(void** comm_out, int nranks, const char id[128], int rank);
+int eodm_comm_destroy(void* comm);
+
+/* ---- one-call step with HOST buffers (what a plugin user times end to end) ---- */
+/* Owns device buffers, pinned staging and a stream for batches up to [maxB, maxT]. */
+typedef struct eodm_session eodm_session;
+int eodm_session_create(const eodm_table* t, const float* py_host, int maxB, int maxT, eodm_session** out);
+void eodm_session_destroy(eodm_session* s);
+/* The stream the session enqueues on (a cudaStream_t). */
+void* eodm_session_stream(eodm_session* s);
+/* The same step on DEVICE buffers the caller already holds (a TF custom op, a CUDA graph):
+ * softmax -> counts -> [allreduce] -> loss -> counts VJP -> softmax VJP, enqueued on `stream`
+ * with the session's scratch; no copies, no synchronisation.  loss f32[1], dlogits
+ * f32[B][T][V] (NULL = forward only) are device pointers. */
+int eodm_session_step_device(eodm_session* s, const float* logits, const uint8_t* mask, int B, int T, void* comm,
+                             float* loss, float* dlogits, void* stream);
+/* Page-locked host memory for callers with no CUDA binding of their own. */
+int eodm_host_alloc(size_t bytes, void** out);
+int eodm_host_free(void* p);
+/* EODM_loss (models/EODM.py:5-25) forward + gradient wrt `_logits`:
+ * H2D(logits, mask) -> softmax -> counts -> [allreduce if comm != NULL] -> loss -> counts VJP
+ * -> softmax VJP -> D2H(loss, dlogits).  dlogits_host may be NULL (forward only).
+ * Synchronises the session's stream before returning. */
+int eodm_session_loss(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
+                      void* comm, float* loss_host, float* dlogits_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EODM_B200_H_ */

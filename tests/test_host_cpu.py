@@ -1,0 +1,251 @@
+"""CPU suite: oracle vs the golden vectors, host logic (table producers, trie
+builder, walk logic through the emulator), C-ABI symbols.  No GPU compute."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import eodm_oracle as O
+from tests import trie_emulator as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ---------------------------------------------------------------- oracle vs golden
+def test_oracle_table_checksums(golden):
+    # SURVEY.md section 8c known answers, produced by the reference's own read_ngram/ngram2kernel
+    assert sha16(golden["timit1000_ids"]) == "4fd163c05ffe37a3"
+    assert sha16(golden["timit1000_py"]) == "3f137490c4e79c08"
+    assert sha16(golden["timit10000_ids"]) == "931b66e24038c5f7"
+    assert sha16(golden["timit10000_py"]) == "5628438b35cc0c76"
+    assert int(golden["timit1000_total"]) == 41147 and int(golden["timit10000_total"]) == 91786
+    assert tuple(golden["timit1000_ids"][0]) == (1, 9, 2, 29, 1)
+    assert float(golden["timit1000_py"][0]) == 0.011033611372113228
+
+
+def test_oracle_ngram2kernel_matches_reference(golden):
+    for K in (1000, 10000):
+        ids, py = golden["timit%d_ids" % K], golden["timit%d_py" % K]
+        ngram = [(tuple(int(v) for v in z), float(p)) for z, p in zip(ids, py.astype(np.float64))]
+        kernel, py2 = O.ngram2kernel(ngram, O.Args(5, K, 40))
+        assert sha16(kernel) == str(golden["timit%d_kernel_sha" % K])
+        assert int((kernel != 0).sum()) == int(golden["timit%d_kernel_nnz" % K])
+        assert np.array_equal(py2, py)
+        assert np.array_equal(O.kernel_to_ids(kernel), ids)
+        assert np.array_equal(O.ids_to_kernel(ids, 40), kernel)
+
+
+def _case(golden, tag):
+    if tag == "C":
+        kernel, py, n = golden["C_kernel"], golden["C_py"], 3
+    else:
+        ids = golden["timit1000_ids"]
+        kernel, py, n = O.ids_to_kernel(ids, 40), golden["timit1000_py"], 5
+    return kernel, O.kernel_to_ids(kernel), py, n, golden[tag + "_logits"], golden[tag + "_mask"]
+
+
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_oracle_direct_matches_reference_graph(golden, tag):
+    """O2 (gather-product + analytic backward, fp64) against the reference's own
+    EODM_loss source executed through the torch shim (fp64 goldens)."""
+    kernel, ids, py, n, logits, mask = _case(golden, tag)
+    r = O.eodm_loss_direct(logits, mask, ids, n, py)
+    assert abs(r["loss"] - golden[tag + "_loss_f64"]) <= 1e-12 * abs(golden[tag + "_loss_f64"])
+    ref = golden[tag + "_dlogits_f64"]
+    assert np.abs(r["dlogits"] - ref).max() <= 1e-10 * np.abs(ref).max()
+    # first 8 filters of P_Ngram's output
+    pz = next(O.window_products(O.softmax(logits), ids, n, batch_chunk=logits.shape[0]))[2][:, :, :8]
+    assert np.allclose(pz, golden[tag + "_pz_f64"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("tag", ["A", "C"])
+def test_oracle_literal_fp32_matches_reference_graph(golden, tag):
+    kernel, ids, py, n, logits, mask = _case(golden, tag)
+    r = O.eodm_loss_literal(logits, mask, kernel, py, dtype="float32")
+    assert abs(float(r["loss"]) - float(golden[tag + "_loss_f32"])) <= 2e-6 * abs(float(golden[tag + "_loss_f32"]))
+    ref = golden[tag + "_dlogits_f32"]
+    assert np.abs(r["dlogits"] - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_oracle_known_answer_uniform():
+    # uniform posterior, full mask -> loss = n ln V - ln((T-n+1)/T)
+    V, n, K, B, T = 40, 5, 50, 3, 17
+    ids, py = O.synth_table(V, n, K, seed=3)
+    r = O.eodm_loss_direct(np.zeros((B, T, V), np.float32), np.ones((B, T), bool), ids, n, py)
+    # = n ln V - ln((T-n+1)/T) up to the two 1e-15 terms and the f32 rounding of sum(py)
+    want = -np.log((T - n + 1) / T * (1.0 / V + 1e-15) ** n + 1e-15) * float(py.astype(np.float64).sum())
+    assert abs(r["loss"] - want) < 1e-12 * want
+    assert abs(r["loss"] - (n * np.log(V) - np.log((T - n + 1) / T))) < 1e-6
+
+
+def test_oracle_finite_differences():
+    rng = np.random.default_rng(0)
+    V, n, K, B, T = 7, 3, 20, 2, 6
+    ids, py = O.synth_table(V, n, K, seed=1, min_id=0)
+    ids[3, 2] = -1
+    ids[5, 1:] = -1
+    logits = rng.standard_normal((B, T, V))
+    mask = np.array([[1, 1, 1, 1, 1, 0], [1, 1, 1, 0, 0, 0]], bool)
+    r = O.eodm_loss_direct(logits, mask, ids, n, py)
+    h = 1e-6
+    for (b, t, v) in [(0, 0, 0), (0, 4, 3), (1, 2, 6), (1, 5, 1), (0, 5, 2)]:
+        lp, lm = logits.copy(), logits.copy()
+        lp[b, t, v] += h
+        lm[b, t, v] -= h
+        fd = (O.eodm_loss_direct(lp, mask, ids, n, py)["loss"] - O.eodm_loss_direct(lm, mask, ids, n, py)["loss"]) / (2 * h)
+        assert abs(fd - r["dlogits"][b, t, v]) < 1e-6 * max(1.0, abs(fd))
+
+
+# ---------------------------------------------------------------- product host logic
+def test_tools_match_oracle_and_golden(eodm, golden, tmp_path):
+    # a small n-gram file in the reference's format, including the unigram parse quirk
+    vocab = tmp_path / "v.vocab"
+    vocab.write_text("<pad> 0\nsil 1\naa 2\nb 3\n")
+    ng = tmp_path / "x.ngram"
+    ng.write_text("('sil', 'aa', 'b'):30\n('aa', 'zz', 'sil'):20\n('sil',):10\n('b', 'b', 'b'):5\n")
+    t2i, i2t = eodm.load_vocab(str(vocab))
+    t2i_o, _ = O.load_vocab(str(vocab))
+    got, tot = eodm.read_ngram(3, str(ng), t2i)
+    want, tot_o = O.read_ngram(3, str(ng), t2i_o)
+    assert got == want and tot == tot_o == 60
+    assert got[1][0] == (2, 0, 1)        # unknown token -> 0
+    assert got[2][0] == (0,)             # ('sil',) mis-parsed exactly like the reference
+    assert eodm.read_ngram(2, str(ng), t2i, type="dict") == O.read_ngram(2, str(ng), t2i_o, type="dict")
+    args = O.Args(3, 4, 4)
+    k1, p1 = eodm.ngram2kernel(got, args)
+    k2, p2 = O.ngram2kernel(want, args)
+    assert np.array_equal(k1, k2) and np.array_equal(p1, p2) and k1.dtype == np.float32 and p1.dtype == np.float32
+    assert p1.shape == (3,) and k1.shape == (3, 4, 4)       # len(ngram) < top_k: py shorter than K, like the reference
+    with pytest.raises(IndexError):
+        eodm.ngram2kernel([((1, 2, 3, 1), 1.0)], args)      # n-gram longer than args.data.ngram
+    # golden: shipped TIMIT table
+    ids, py = golden["timit1000_ids"], golden["timit1000_py"]
+    ngram = [(tuple(int(v) for v in z), float(p)) for z, p in zip(ids, py.astype(np.float64))]
+    kernel, py2 = eodm.ngram2kernel(ngram, O.Args(5, 1000, 40))
+    assert sha16(kernel) == str(golden["timit1000_kernel_sha"]) and np.array_equal(py2, py)
+    assert np.array_equal(eodm.ngram_ids(ngram, 5), ids)
+
+
+def test_table_round_trip_bit_exact(eodm, golden):
+    for K in (1000, 10000):
+        ids = golden["timit%d_ids" % K]
+        kernel = O.ids_to_kernel(ids, 40)
+        t = eodm.NgramTable.from_dense(kernel, device=-1)
+        got_ids, order = t.ids()
+        assert np.array_equal(got_ids, ids) and np.all(order == 5)
+        assert sha16(t.to_dense()) == str(golden["timit%d_kernel_sha" % K])
+        t2 = eodm.NgramTable.from_ids(ids, 40, device=-1)
+        assert np.array_equal(t2.to_dense(), kernel)
+    # mixed orders (golden case C) incl. trailing zero columns
+    t = eodm.NgramTable.from_dense(golden["C_kernel"], device=-1)
+    assert np.array_equal(t.to_dense(), golden["C_kernel"])
+    assert np.array_equal(t.ids()[0], O.kernel_to_ids(golden["C_kernel"]))
+
+
+def test_table_rejects_bad_kernels(eodm):
+    k = np.zeros((3, 5, 4), np.float32)
+    k[0, 1, 0] = 1
+    k[0, 2, 0] = 1                                   # two non-zeros in a column
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.NgramTable.from_dense(k, device=-1)
+    assert e.value.status == -1 and "one-hot" in str(e.value)
+    k[0, 2, 0] = 0.5
+    k[0, 1, 0] = 0
+    with pytest.raises(eodm.EodmError):
+        eodm.NgramTable.from_dense(k, device=-1)     # neither 0 nor 1
+    k[:] = 0
+    k[1, 1, 0] = 1                                   # gap before position 1
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.NgramTable.from_dense(k, device=-1)
+    assert e.value.status == -5
+    with pytest.raises(eodm.EodmError):
+        eodm.NgramTable.from_ids(np.array([[1, 7, 0]], np.int32), 5, device=-1)   # id >= V
+
+
+def _random_case(seed, V, n, K, B, T, mixed, dup=False):
+    rng = np.random.default_rng(seed)
+    ids, py = O.synth_table(V, n, K, seed=seed, min_id=0)
+    if mixed:
+        for z in range(K):
+            o = int(rng.integers(0 if z % 7 == 0 else 1, n + 1))
+            ids[z, o:] = -1
+    if dup:
+        ids[K // 2] = ids[0]
+        ids[K - 1] = ids[1]
+    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=1)
+    mask[0, :] = False            # an all-padding utterance
+    mask[-1, :] = True
+    return ids, py, logits, mask
+
+
+@pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", [
+    (1, 9, 3, 40, 3, 9, False, False),
+    (2, 6, 4, 70, 2, 11, True, False),
+    (3, 5, 2, 20, 4, 5, True, True),
+    (4, 12, 1, 10, 2, 4, False, False),
+    (5, 7, 5, 300, 2, 8, True, True),
+    (6, 40, 3, 2000, 1, 6, False, False),
+])
+def test_trie_walk_emulation_matches_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
+    """table.cc tries + the kernels' walk logic (emulated) == oracle, forward and backward."""
+    ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
+    t = eodm.NgramTable.from_ids(ids, V, device=-1)
+    px = O.softmax(logits)
+    S_ref, N = O.counts_fwd(px, mask, ids, n)
+    S = E.emulate_fwd(t, px, mask)
+    assert np.allclose(S, S_ref, rtol=1e-12, atol=1e-300)
+    gS = np.random.default_rng(seed).standard_normal(K)
+    d_ref = O.counts_bwd(px, mask, ids, n, gS)
+    d = E.emulate_bwd(t, px, mask, gS)
+    assert np.abs(d - d_ref).max() <= 1e-12 * max(1e-300, np.abs(d_ref).max())
+
+
+def test_trie_sizes_timit(eodm, golden):
+    # prefix sharing quoted in SURVEY.md 8c for the shipped table: 242/518/779 distinct 2/3/4-prefixes
+    t = eodm.NgramTable.from_ids(golden["timit1000_ids"], 40, device=-1)
+    tr = t.debug_trie(0)
+    assert len(tr["units"]) == 242 and len(tr["perm"]) == 1000
+    assert len(tr["nodes"]) == 242 + 518 + 779 + 1000
+    assert sorted(tr["perm"].tolist()) == list(range(1000))
+
+
+# ---------------------------------------------------------------- C ABI surface
+def test_cabi_exports_every_declared_symbol(eodm):
+    hdr = open(os.path.join(ROOT, "include", "eodm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(eodm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 28
+    raw = C.CDLL(eodm.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), "libeodm_b200.so does not export %s" % name
+    from eodm_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert raw.eodm_version() == 100
+
+
+def test_no_cpu_fallback(eodm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ids, py = O.synth_table(8, 2, 10, seed=0)
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.NgramTable.from_ids(ids, 8, device=0)            # needs a CUDA device
+    assert e.value.status == -3 and "no CPU path" in str(e.value)
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, 8, device=-1))
+    with pytest.raises(eodm.EodmError):
+        eodm.EODM_loss(torch.zeros(2, 5, 8), torch.ones(2, 5, dtype=torch.bool), conv_op, 10, py)
+    with pytest.raises(TypeError):
+        eodm.EODM_loss(torch.zeros(2, 5, 8), torch.ones(2, 5), lambda x: x, 10, py)
+    # product code never imports the oracle
+    pkg = os.path.join(ROOT, "unsupervised-asr_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cc", ".cu", ".h")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace("# oracle-free", ""), f

@@ -1,0 +1,343 @@
+// C ABI of libeodm_b200.so (see include/eodm_b200.h): argument checking, the
+// NCCL binding for the batch-sharded step, and the host-buffer session.
+#include <cuda_runtime_api.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "../../include/eodm_b200.h"
+#include "kernels.h"
+#include "table.h"
+
+#define REQUIRE(cond, code, ...)    \
+  do {                              \
+    if (!(cond)) {                  \
+      eodm_set_error(__VA_ARGS__);  \
+      return code;                  \
+    }                               \
+  } while (0)
+
+#define CUDA_TRY(expr)                                                     \
+  do {                                                                     \
+    cudaError_t e_ = (expr);                                               \
+    if (e_ != cudaSuccess) {                                               \
+      eodm_set_error("%s failed: %s", #expr, cudaGetErrorString(e_));      \
+      return EODM_ECUDA;                                                   \
+    }                                                                      \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int eodm_version(void) { return EODM_B200_VERSION; }
+
+static int check_batch(const eodm_table* t, const void* px, const void* mask, int B, int T) {
+  REQUIRE(t && px && mask, EODM_EINVAL, "null pointer");
+  REQUIRE(t->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
+  REQUIRE(B >= 1 && T >= 1, EODM_ESHAPE, "need B >= 1 and T >= 1 (B=%d T=%d)", B, T);
+  REQUIRE(T >= t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, t->n);
+  REQUIRE(aligned16(px), EODM_EINVAL, "px must be 16-byte aligned");
+  return EODM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// counts, loss, softmax, materialising op
+// ---------------------------------------------------------------------------
+extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
+  (void)B;
+  (void)T;
+  if (!t || t->device < 0) return 0;
+  return eodm_counts_workspace_bytes(t);
+}
+
+extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
+                               float* N, void* ws, void* stream) {
+  int rc = check_batch(t, px, mask, B, T);
+  if (rc != EODM_OK) return rc;
+  REQUIRE(S && ws, EODM_EINVAL, "null pointer");
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, ws, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                               const float* gS, float* dpx, void* ws, void* stream) {
+  int rc = check_batch(t, px, mask, B, T);
+  if (rc != EODM_OK) return rc;
+  REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
+  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_loss_from_counts(const float* S, const float* N, const float* py, int K, float eps, float* loss,
+                                     float* gS, void* stream) {
+  REQUIRE(S && N && py && loss, EODM_EINVAL, "null pointer");
+  REQUIRE(K >= 1, EODM_ESHAPE, "K=%d", K);
+  return eodm_loss_launch(S, N, py, K, eps, loss, gS, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_softmax_fwd(const float* logits, int64_t rows, int V, float* px, void* stream) {
+  REQUIRE(logits && px, EODM_EINVAL, "null pointer");
+  REQUIRE(rows >= 0 && V >= 1, EODM_ESHAPE, "rows=%lld V=%d", (long long)rows, V);
+  REQUIRE((rows + 7) / 8 <= 0x7fffffffLL, EODM_EUNSUPPORTED, "too many rows");
+  return eodm_softmax_fwd_launch(logits, rows, V, px, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_softmax_bwd(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, void* stream) {
+  REQUIRE(px && dpx && dlogits, EODM_EINVAL, "null pointer");
+  REQUIRE(rows >= 0 && V >= 1, EODM_ESHAPE, "rows=%lld V=%d", (long long)rows, V);
+  REQUIRE((rows + 7) / 8 <= 0x7fffffffLL, EODM_EUNSUPPORTED, "too many rows");
+  return eodm_softmax_bwd_launch(px, dpx, rows, V, dlogits, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_prob_fwd(const eodm_table* t, const float* px, int B, int T, float* p, void* stream) {
+  REQUIRE(t && px && p, EODM_EINVAL, "null pointer");
+  REQUIRE(t->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
+  REQUIRE(B >= 1 && T >= t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, t->n);
+  return eodm_prob_fwd_launch(t, px, B, T, p, (cudaStream_t)stream);
+}
+
+extern "C" int eodm_prob_bwd(const eodm_table* t, const float* px, const float* dp, int B, int T, float* dpx,
+                             void* stream) {
+  REQUIRE(t && px && dp && dpx, EODM_EINVAL, "null pointer");
+  REQUIRE(t->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
+  REQUIRE(B >= 1 && T >= t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, t->n);
+  return eodm_prob_bwd_launch(t, px, dp, B, T, dpx, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at first use (the library itself links only the CUDA runtime)
+// ---------------------------------------------------------------------------
+namespace {
+struct Nccl {
+  struct Uid {  // ncclUniqueId is passed BY VALUE: 128 opaque bytes
+    char b[128];
+  };
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+Nccl g_nccl;
+std::once_flag g_nccl_once;
+
+void nccl_load() {
+  const char* env = getenv("EODM_NCCL_LIB");
+  const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.h, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce &&
+              g_nccl.GetErrorString;
+}
+
+int nccl_ready() {
+  std::call_once(g_nccl_once, nccl_load);
+  if (!g_nccl.ok) {
+    eodm_set_error("NCCL not found (dlopen libnccl.so.2 failed; set EODM_NCCL_LIB to its path)");
+    return EODM_ENCCL;
+  }
+  return EODM_OK;
+}
+
+int nccl_check(int r, const char* what) {
+  if (r == 0) return EODM_OK;
+  eodm_set_error("%s failed: %s", what, g_nccl.GetErrorString(r));
+  return EODM_ENCCL;
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+}  // namespace
+
+extern "C" int eodm_comm_unique_id(char id_out[128]) {
+  REQUIRE(id_out, EODM_EINVAL, "null pointer");
+  int rc = nccl_ready();
+  if (rc != EODM_OK) return rc;
+  return nccl_check(g_nccl.GetUniqueId(id_out), "ncclGetUniqueId");
+}
+
+extern "C" int eodm_comm_init(void** comm_out, int nranks, const char id[128], int rank) {
+  REQUIRE(comm_out && id, EODM_EINVAL, "null pointer");
+  REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, EODM_EINVAL, "bad rank %d of %d", rank, nranks);
+  int rc = nccl_ready();
+  if (rc != EODM_OK) return rc;
+  Nccl::Uid uid;
+  memcpy(uid.b, id, 128);
+  return nccl_check(g_nccl.CommInitRank(comm_out, nranks, uid, rank), "ncclCommInitRank");
+}
+
+extern "C" int eodm_comm_destroy(void* comm) {
+  if (!comm) return EODM_OK;
+  int rc = nccl_ready();
+  if (rc != EODM_OK) return rc;
+  return nccl_check(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+
+extern "C" int eodm_allreduce_counts(void* comm, float* S, int K, float* N, void* stream) {
+  REQUIRE(comm && S, EODM_EINVAL, "null pointer");
+  REQUIRE(K >= 1, EODM_ESHAPE, "K=%d", K);
+  int rc = nccl_ready();
+  if (rc != EODM_OK) return rc;
+  if (N == S + K) {  // packed [S, N]: one collective
+    return nccl_check(g_nccl.AllReduce(S, S, (size_t)K + 1, kNcclFloat32, kNcclSum, comm, (cudaStream_t)stream),
+                      "ncclAllReduce");
+  }
+  rc = nccl_check(g_nccl.AllReduce(S, S, (size_t)K, kNcclFloat32, kNcclSum, comm, (cudaStream_t)stream),
+                  "ncclAllReduce");
+  if (rc != EODM_OK || !N) return rc;
+  return nccl_check(g_nccl.AllReduce(N, N, 1, kNcclFloat32, kNcclSum, comm, (cudaStream_t)stream), "ncclAllReduce");
+}
+
+// ---------------------------------------------------------------------------
+// dense bigram path (tcgen05): built in bigram.cu when present
+// ---------------------------------------------------------------------------
+#ifndef EODM_HAVE_BIGRAM
+extern "C" size_t eodm_bigram_workspace_bytes(int, int, int) { return 0; }
+extern "C" int eodm_bigram_dense_fwd(const float*, const uint8_t*, int, int, int, float*, float*, void*, void*) {
+  eodm_set_error("dense bigram path is not part of this build");
+  return EODM_EUNSUPPORTED;
+}
+extern "C" int eodm_bigram_dense_bwd(const float*, const uint8_t*, int, int, int, const float*, float*, void*, void*) {
+  eodm_set_error("dense bigram path is not part of this build");
+  return EODM_EUNSUPPORTED;
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// session: EODM_loss forward + gradient wrt logits in one call
+// ---------------------------------------------------------------------------
+struct eodm_session {
+  const eodm_table* t;
+  int maxB, maxT, device;
+  cudaStream_t st;
+  float *logits, *px, *dpx, *dlogits;
+  float* counts;  // [K + 1]: S then N (packed for one all-reduce)
+  float *py, *gS, *loss;
+  uint8_t* mask;
+  void* ws;
+};
+
+static void session_free(eodm_session* s) {
+  if (!s) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(s->device);
+  void* ptrs[] = {s->logits, s->px, s->dpx, s->dlogits, s->counts, s->py, s->gS, s->loss, s->mask, s->ws};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (s->st) cudaStreamDestroy(s->st);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete s;
+}
+
+extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, int maxB, int maxT, eodm_session** out) {
+  REQUIRE(t && py_host && out, EODM_EINVAL, "null pointer");
+  REQUIRE(t->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
+  REQUIRE(maxB >= 1 && maxT >= t->n, EODM_ESHAPE, "maxB=%d maxT=%d (kernel_size %d)", maxB, maxT, t->n);
+  *out = nullptr;
+  eodm_session* s = new (std::nothrow) eodm_session();
+  REQUIRE(s, EODM_ENOMEM, "out of host memory");
+  memset(s, 0, sizeof(*s));
+  s->t = t;
+  s->maxB = maxB;
+  s->maxT = maxT;
+  s->device = t->device;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  const size_t rows = (size_t)maxB * maxT, el = rows * t->V * sizeof(float);
+  cudaError_t e = cudaSetDevice(t->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->logits, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->px, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->dpx, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->dlogits, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->mask, rows);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts, ((size_t)t->K + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->py, (size_t)t->K * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->gS, (size_t)t->K * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&s->ws, eodm_counts_workspace_bytes(t));
+  if (e == cudaSuccess) e = cudaMemcpy(s->py, py_host, (size_t)t->K * sizeof(float), cudaMemcpyHostToDevice);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    eodm_set_error("session allocation failed: %s", cudaGetErrorString(e));
+    session_free(s);
+    return e == cudaErrorMemoryAllocation ? EODM_ENOMEM : EODM_ECUDA;
+  }
+  *out = s;
+  return EODM_OK;
+}
+
+extern "C" void eodm_session_destroy(eodm_session* s) { session_free(s); }
+
+extern "C" void* eodm_session_stream(eodm_session* s) { return s ? (void*)s->st : nullptr; }
+
+extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, const uint8_t* mask, int B, int T,
+                                        void* comm, float* loss, float* dlogits, void* stream) {
+  REQUIRE(s && logits && mask && loss, EODM_EINVAL, "null pointer");
+  REQUIRE(B >= 1 && B <= s->maxB && T <= s->maxT, EODM_ESHAPE, "batch [%d,%d] exceeds the session's [%d,%d]", B, T,
+          s->maxB, s->maxT);
+  const eodm_table* t = s->t;
+  REQUIRE(T >= t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, t->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)B * T;
+  float* S = s->counts;
+  float* N = s->counts + t->K;
+  int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
+  if (rc == EODM_OK) rc = eodm_counts_fwd_launch(t, s->px, mask, B, T, S, N, s->ws, st);
+  if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, S, t->K, N, st);
+  if (rc == EODM_OK) rc = eodm_loss_launch(S, N, s->py, t->K, 1e-15f, loss, dlogits ? s->gS : nullptr, st);
+  if (rc == EODM_OK && dlogits) rc = eodm_counts_bwd_launch(t, s->px, mask, B, T, s->gS, s->dpx, s->ws, st);
+  if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(s->px, s->dpx, rows, t->V, dlogits, st);
+  return rc;
+}
+
+extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
+                                 void* comm, float* loss_host, float* dlogits_host) {
+  REQUIRE(s && logits_host && mask_host && loss_host, EODM_EINVAL, "null pointer");
+  REQUIRE(B >= 1 && B <= s->maxB && T >= 1 && T <= s->maxT, EODM_ESHAPE,
+          "batch [%d,%d] exceeds the session's [%d,%d]", B, T, s->maxB, s->maxT);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(s->device));
+  const size_t rows = (size_t)B * T, el = rows * s->t->V * sizeof(float);
+  int rc = EODM_OK;
+  cudaError_t e = cudaMemcpyAsync(s->logits, logits_host, el, cudaMemcpyHostToDevice, s->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->mask, mask_host, rows, cudaMemcpyHostToDevice, s->st);
+  if (e == cudaSuccess)
+    rc = eodm_session_step_device(s, s->logits, s->mask, B, T, comm, s->loss, dlogits_host ? s->dlogits : nullptr,
+                                  s->st);
+  if (e == cudaSuccess && rc == EODM_OK && dlogits_host)
+    e = cudaMemcpyAsync(dlogits_host, s->dlogits, el, cudaMemcpyDeviceToHost, s->st);
+  if (e == cudaSuccess && rc == EODM_OK)
+    e = cudaMemcpyAsync(loss_host, s->loss, sizeof(float), cudaMemcpyDeviceToHost, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamSynchronize(s->st);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (rc != EODM_OK) return rc;
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_session_loss: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
+
+// pinned host memory for callers without a CUDA binding of their own
+extern "C" int eodm_host_alloc(size_t bytes, void** out) {
+  REQUIRE(out, EODM_EINVAL, "null pointer");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return EODM_OK;
+}
+extern "C" int eodm_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return EODM_OK;
+}

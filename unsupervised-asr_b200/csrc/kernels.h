@@ -1,0 +1,27 @@
+// Internal launch entry points shared between the .cu files and the C ABI (api.cc).
+#ifndef EODM_KERNELS_H_
+#define EODM_KERNELS_H_
+
+#include <cuda_runtime_api.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct eodm_table;
+
+// counts.cu -- CUDA-core trie path
+size_t eodm_counts_workspace_bytes(const eodm_table* t);
+int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
+                           void* ws, cudaStream_t st);
+int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
+                           float* dpx, void* ws, cudaStream_t st);
+
+// ops.cu -- loss, softmax, materialising op
+int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
+                     cudaStream_t st);
+int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st);
+int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st);
+int eodm_prob_fwd_launch(const eodm_table* t, const float* px, int B, int T, float* p, cudaStream_t st);
+int eodm_prob_bwd_launch(const eodm_table* t, const float* px, const float* dp, int B, int T, float* dpx,
+                         cudaStream_t st);
+
+#endif

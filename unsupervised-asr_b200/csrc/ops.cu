@@ -1,0 +1,194 @@
+// The small kernels either side of the counts: the loss from the counts
+// (models/EODM.py:20-23), softmax and its VJP (models/EODM.py:15), and the
+// materialising op P_Ngram.__call__ (models/EODM.py:63-71) with its VJP.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/eodm_b200.h"
+#include "kernels.h"
+#include "table.h"
+
+namespace {
+
+constexpr float kEps = 1e-15f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// loss = -sum_z py[z] * log(S[z]/N + eps);  gS[z] = -py[z] / (S[z]/N + eps) / N.
+// One CTA, fixed summation order.
+__global__ void __launch_bounds__(1024) eodm_loss_kernel(const float* __restrict__ S, const float* __restrict__ N,
+                                                         const float* __restrict__ py, int K, float eps,
+                                                         float* __restrict__ loss, float* __restrict__ gS) {
+  __shared__ float red[32];
+  const float n = N[0];
+  float acc = 0.f;
+  for (int z = threadIdx.x; z < K; z += blockDim.x) {
+    const float pz = S[z] / n;
+    const float p = py[z];
+    acc += -p * logf(pz + eps);
+    if (gS) gS[z] = -p / (pz + eps) / n;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v;
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) eodm_softmax_fwd_kernel(const float* __restrict__ x, int64_t rows, int V,
+                                                               float* __restrict__ y) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * V;
+  float* yr = y + row * V;
+  float m = -FLT_MAX;
+  for (int v = lane; v < V; v += 32) m = fmaxf(m, xr[v]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int v = lane; v < V; v += 32) s += expf(xr[v] - m);
+  s = warp_sum(s);
+  for (int v = lane; v < V; v += 32) yr[v] = expf(xr[v] - m) / s;
+}
+
+// dlogits = px * (dpx - sum_v px*dpx)
+__global__ void __launch_bounds__(256) eodm_softmax_bwd_kernel(const float* __restrict__ px,
+                                                               const float* __restrict__ dpx, int64_t rows, int V,
+                                                               float* __restrict__ dx) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = px + row * V;
+  const float* d = dpx + row * V;
+  float s = 0.f;
+  for (int v = lane; v < V; v += 32) s = fmaf(p[v], d[v], s);
+  s = warp_sum(s);
+  for (int v = lane; v < V; v += 32) dx[row * V + v] = p[v] * (d[v] - s);
+}
+
+// p[b][t][z] = prod_{j < order[z]} (px[b][t+j][ids[z][j]] + eps)
+__global__ void __launch_bounds__(256) eodm_prob_fwd_kernel(const float* __restrict__ px,
+                                                            const int32_t* __restrict__ ids, int n, int V, int K,
+                                                            int T, int Tp, float* __restrict__ p) {
+  const int64_t w = blockIdx.x;  // window index b*Tp + t
+  const int b = (int)(w / Tp), t = (int)(w - (int64_t)b * Tp);
+  const float* base = px + ((int64_t)b * T + t) * V;
+  for (int z = threadIdx.x; z < K; z += blockDim.x) {
+    float q = 1.f;
+    for (int j = 0; j < n; ++j) {
+      const int v = ids[(int64_t)z * n + j];
+      if (v < 0) break;
+      q *= __ldg(base + (int64_t)j * V + v) + kEps;
+    }
+    p[w * K + z] = q;
+  }
+}
+
+// dpx[b][s][v] = sum_{(z,j): ids[z][j]==v, 0<=s-j<=T-n} dp[b][s-j][z] * prod_{j'!=j}(px[b][s-j+j'][ids[z][j']] + eps)
+// One thread per (row, v), gathering through the inverse index: deterministic, no atomics.
+__global__ void __launch_bounds__(256) eodm_prob_bwd_kernel(const float* __restrict__ px, const float* __restrict__ dp,
+                                                            const int32_t* __restrict__ ids,
+                                                            const int32_t* __restrict__ inv_off,
+                                                            const int32_t* __restrict__ inv_zj, int n, int V, int K,
+                                                            int T, int Tp, int64_t total, float* __restrict__ dpx) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % V);
+  const int64_t row = idx / V;
+  const int s = (int)(row % T);
+  const int64_t b = row / T;
+  float acc = 0.f;
+  const int e1 = inv_off[v + 1];
+  for (int e = inv_off[v]; e < e1; ++e) {
+    const int zj = inv_zj[e];
+    const int z = zj / EODM_MAX_N, j = zj % EODM_MAX_N;
+    const int t = s - j;
+    if (t < 0 || t >= Tp) continue;
+    float q = dp[(b * Tp + t) * K + z];
+    const float* base = px + (b * T + t) * V;
+    for (int jj = 0; jj < n; ++jj) {
+      const int vv = ids[(int64_t)z * n + jj];
+      if (vv < 0) break;
+      if (jj != j) q *= __ldg(base + (int64_t)jj * V + vv) + kEps;
+    }
+    acc += q;
+  }
+  dpx[idx] = acc;
+}
+
+}  // namespace
+
+#define EODM_CHECK_LAUNCH(name)                                                   \
+  do {                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                          \
+    if (e_ != cudaSuccess) {                                                      \
+      eodm_set_error(name " launch failed: %s", cudaGetErrorString(e_));          \
+      return EODM_ECUDA;                                                          \
+    }                                                                             \
+  } while (0)
+
+int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
+                     cudaStream_t st) {
+  eodm_loss_kernel<<<1, 1024, 0, st>>>(S, N, py, K, eps, loss, gS);
+  EODM_CHECK_LAUNCH("eodm_loss_kernel");
+  return EODM_OK;
+}
+
+int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st) {
+  if (rows == 0) return EODM_OK;
+  const int wpb = 8;
+  eodm_softmax_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(logits, rows, V, px);
+  EODM_CHECK_LAUNCH("eodm_softmax_fwd_kernel");
+  return EODM_OK;
+}
+
+int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st) {
+  if (rows == 0) return EODM_OK;
+  const int wpb = 8;
+  eodm_softmax_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(px, dpx, rows, V, dlogits);
+  EODM_CHECK_LAUNCH("eodm_softmax_bwd_kernel");
+  return EODM_OK;
+}
+
+int eodm_prob_fwd_launch(const eodm_table* t, const float* px, int B, int T, float* p, cudaStream_t st) {
+  const int Tp = T - t->n + 1;
+  const int64_t W = (int64_t)B * Tp;
+  if (W == 0) return EODM_OK;
+  if (W > 0x7fffffffLL) {
+    eodm_set_error("B*(T-n+1) too large for the materialising op");
+    return EODM_EUNSUPPORTED;
+  }
+  eodm_prob_fwd_kernel<<<(unsigned)W, 256, 0, st>>>(px, t->d_ids, t->n, t->V, t->K, T, Tp, p);
+  EODM_CHECK_LAUNCH("eodm_prob_fwd_kernel");
+  return EODM_OK;
+}
+
+int eodm_prob_bwd_launch(const eodm_table* t, const float* px, const float* dp, int B, int T, float* dpx,
+                         cudaStream_t st) {
+  const int Tp = T - t->n + 1;
+  const int64_t total = (int64_t)B * T * t->V;
+  if (total == 0) return EODM_OK;
+  const int64_t blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffLL) {
+    eodm_set_error("B*T*V too large for the materialising op");
+    return EODM_EUNSUPPORTED;
+  }
+  eodm_prob_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(px, dp, t->d_ids, t->d_inv_off, t->d_inv_zj, t->n, t->V, t->K,
+                                                         T, Tp, total, dpx);
+  EODM_CHECK_LAUNCH("eodm_prob_bwd_kernel");
+  return EODM_OK;
+}
