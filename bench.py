@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""EODM fwd+bwd throughput (frames/s) on B200, with the roofline of the dominant
+kernel and the reference's CPU formulation timed beside it.
+
+    python bench.py --gpus 1 --steps 30 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 5 --warmup 1      # the CPU arm
+
+A step = one pass of the hot path over one synthetic batch: softmax ->
+expected n-gram counts -> [all-reduce of K+1 floats] -> loss and dloss/dS ->
+counts VJP -> softmax VJP (the EODM_loss boundary: `_logits` in, loss and
+dloss/d_logits out; models/EODM.py:5-25 + the tape of main_EODM.py:168).
+Workload at N=1: BASELINE.json configs[1] (B=256, T=400, V=48, trigram top-10k);
+at N>1 every rank runs that shape on its own batch (weak scaling) and the ranks
+exchange the partial counts over NCCL.  frames = valid posterior rows.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "unsupervised-asr_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+L2_FLUSH_BYTES = 256 << 20
+CPU_SAMPLE_B = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="timit_c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference formulation (softmax -> log -> dense one-hot Conv1D -> exp -> mask ->
+# reduce -> loss, backward by autodiff) restated op for op on torch-CPU.  TensorFlow is not
+# installable in this image, so this is kind="port" (oracle/eodm_oracle.py:eodm_loss_literal).
+# ---------------------------------------------------------------------------
+def cpu_reference(w, steps, warmup, sample_b=CPU_SAMPLE_B):
+    import torch
+
+    from oracle import eodm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(sample_b, w["B"])
+    logits, mask = w["logits"][:Bs], w["mask"][:Bs]
+    kernel = O.ids_to_kernel(w["ids"], w["V"])
+    frames = int(mask.sum())
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.eodm_loss_literal(logits, mask, kernel, w["py"], dtype="float32", need_grad=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return dict(frames=frames, times=times, cores=cores, sample_b=Bs,
+                sample="first %d of %d utterances of the %s batch (T=%d, V=%d, n=%d, K=%d), fp32, fwd+bwd by autograd; "
+                       "TF-equivalent dense restatement on torch-CPU (TF 2.x not installable in this image)"
+                       % (Bs, w["B"], w["name"], w["T"], w["V"], w["n"], w["K"]))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from eodm_b200 import synth
+    w = synth.workload(args.workload)
+    w["name"] = args.workload
+    r = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
+    sec = sum(r["times"]) / len(r["times"])
+    val = r["frames"] / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "EODM fwd+bwd frames/sec", "value": val, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "B": w["B"], "T": w["T"], "V": w["V"], "n": w["n"], "K": w["K"],
+                   "step": "bounded sample: %d utterances per step" % r["sample_b"]},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as td
+
+    import eodm_b200 as E
+    from eodm_b200 import synth
+    from eodm_b200.session import PinnedArray
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+        comm = E.dist.Comm.from_torch_distributed()
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+
+    w = synth.workload(args.workload, rank=rank)
+    w["name"] = args.workload
+    B, T, V, n, K = w["B"], w["T"], w["V"], w["n"], w["K"]
+    frames = int(w["mask"].sum())
+    table = E.NgramTable.from_ids(w["ids"], V, device=local)
+    sess = E.Session(table, w["py"], B, T)
+    logits_d = torch.tensor(w["logits"], device=dev)
+    mask_d = torch.tensor(w["mask"], device=dev).to(torch.uint8)
+    loss_d = torch.zeros(1, device=dev)
+    dlogits_d = torch.empty_like(logits_d)
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        sess.step_device(logits_d.data_ptr(), mask_d.data_ptr(), B, T, loss_d.data_ptr(), dlogits_d.data_ptr(), stream,
+                         comm=comm)
+
+    def timed(fn, steps, warmup):
+        """Per-step CUDA-event times (ms) with an L2 flush between steps."""
+        for _ in range(warmup):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        t1 = time.perf_counter()
+        return [a.elapsed_time(b) for a, b in evs], t0, t1
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    ms, t0, t1 = timed(step, args.steps, max(3, args.warmup))
+    total_ms = max_over_ranks(sum(ms))
+    ms_per_step = total_ms / args.steps
+    frames_all = frames
+    if world > 1:
+        ft = torch.tensor([frames], dtype=torch.float64, device=dev)
+        td.all_reduce(ft)
+        frames_all = int(ft[0])
+    value = frames_all / (ms_per_step * 1e-3)
+    clocks = sampler.summary(t0, t1) if rank == 0 else None
+
+    # ---- the two counts kernels alone (rank-local; roofline of the dominant one) ----
+    px = E.softmax_fwd(logits_d)
+    counts = torch.empty(K + 1, device=dev)
+    gS = torch.randn(K, device=dev) * 1e-3
+    ksteps = min(args.steps, 20)
+    ms_f, _, _ = timed(lambda: E.counts_fwd(table, px, mask_d, out=counts), ksteps, 3)
+    ms_b, _, _ = timed(lambda: E.counts_bwd(table, px, mask_d, gS), ksteps, 3)
+    t_f, t_b = statistics.mean(ms_f) * 1e-3, statistics.mean(ms_b) * 1e-3
+    # algorithmic flops of the direct gather-product formula: n per (window, n-gram)
+    # forward, 4n-4 backward (n >= 2); windows = valid window starts
+    t_idx = np.arange(T)[None, :]
+    windows = int((w["mask"] & (t_idx <= T - n)).sum())
+    fl_f = float(n) * windows * K
+    fl_b = float(4 * n - 4 if n >= 2 else 1) * windows * K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12          # TFLOP/s, CUDA-core FMA peak at the max SM clock
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom_is_bwd = t_b >= t_f
+    ach = (fl_b / t_b if dom_is_bwd else fl_f / t_f) / 1e12
+    roofline = {
+        "kernel": "eodm_counts_bwd_kernel" if dom_is_bwd else "eodm_counts_fwd_kernel",
+        "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+        "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s); CUDA-core FMA peak, not a tensor or HBM figure"
+                       % ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "fallback 1965 MHz"),
+        "traffic": None,
+        "fwd": {"ms": t_f * 1e3, "flops": fl_f, "tflops": fl_f / t_f / 1e12},
+        "bwd": {"ms": t_b * 1e3, "flops": fl_b, "tflops": fl_b / t_b / 1e12},
+        "path_fwd_bwd": {"ms": (t_f + t_b) * 1e3, "roofline_ms": max((fl_f + fl_b) / (fp32_peak * 1e12),
+                                                                    12.0 * B * T * V / (hbm_peak * 1e9)) * 1e3},
+        "hbm": {"algorithmic_bytes": 12.0 * B * T * V, "peak_gbs": hbm_peak,
+                "achieved_gbs": 12.0 * B * T * V / (t_f + t_b) / 1e9},
+    }
+    roofline["path_fwd_bwd"]["frac"] = roofline["path_fwd_bwd"]["roofline_ms"] / roofline["path_fwd_bwd"]["ms"]
+
+    # ---- end to end through the host-buffer session (H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        h_logits = PinnedArray((B, T, V), np.float32)
+        h_mask = PinnedArray((B, T), np.uint8)
+        h_dl = PinnedArray((B, T, V), np.float32)
+        h_logits.array[...] = w["logits"]
+        h_mask.array[...] = w["mask"]
+        for _ in range(max(3, args.warmup)):
+            sess.loss(h_logits.array, h_mask.array, h_dl.array, comm=comm)
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(args.steps):
+            loss_val = sess.loss(h_logits.array, h_mask.array, h_dl.array, comm=comm)
+        barrier()
+        e_sec = max_over_ranks(time.perf_counter() - te0) / args.steps
+        e2e = {"value": frames_all / e_sec, "unit": "frames/s", "ms_per_step": e_sec * 1e3,
+               "h2d_bytes_per_step": B * T * V * 4 + B * T, "d2h_bytes_per_step": B * T * V * 4 + 4,
+               "loss": loss_val, "api": "eodm_session_loss (C ABI, pinned host buffers)"}
+    if rank == 0:
+        sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(w, 3, 1)
+        best = min(r["times"])
+        cpu = {"value": r["frames"] / best, "unit": "frames/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"] + "; 1 warm-up + best of 3 (%.2f s)" % best}
+
+    if rank == 0:
+        launches_per_step = 6 + n   # softmax, counts fwd, finish, loss, n x permute_g, counts bwd, softmax VJP
+        out = {
+            "metric": "EODM fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
+                       "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
+                       "path": "cuda-core trie walk"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        comm.close()
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

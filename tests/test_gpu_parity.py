@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes binding and the
+P_Ngram / EODM_loss mirror), against the CPU oracle and the committed golden
+vectors.  Tolerance: 1e-5 relative in fp32 (BASELINE.json north_star) --
+loss |d|/|ref|; gradients max|d|/max|ref| and L2-relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import eodm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def rel_max(a, ref):
+    return float(np.abs(np.asarray(a, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def rel_l2(a, ref):
+    return float(np.linalg.norm(np.asarray(a, np.float64).ravel() - ref.ravel()) / max(np.linalg.norm(ref.ravel()), 1e-300))
+
+
+def _loss_and_grad(eodm, kernel_or_ids, V, py, logits, mask, from_ids=False):
+    dev = _dev()
+    if from_ids:
+        conv_op = eodm.PNgram(eodm.NgramTable.from_ids(kernel_or_ids, V, device=0))
+    else:
+        n, V_, K = kernel_or_ids.shape
+        conv_op = eodm.P_Ngram(kernel_or_ids, O.Args(n, K, V_))
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    loss = eodm.EODM_loss(lg, torch.tensor(mask, device=dev), conv_op, conv_op.table.K, torch.tensor(py, device=dev))
+    loss.backward()
+    return float(loss), lg.grad.cpu().numpy(), conv_op
+
+
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_golden_reference_graph(eodm, golden, tag):
+    """EODM_loss + gradient vs the reference's own source run through the torch shim (fp64)."""
+    if tag == "C":
+        kernel, py = golden["C_kernel"], golden["C_py"]
+    else:
+        kernel, py = O.ids_to_kernel(golden["timit1000_ids"], 40), golden["timit1000_py"]
+    loss, grad, _ = _loss_and_grad(eodm, kernel, kernel.shape[1], py, golden[tag + "_logits"], golden[tag + "_mask"])
+    ref_l, ref_g = float(golden[tag + "_loss_f64"]), golden[tag + "_dlogits_f64"]
+    assert abs(loss - ref_l) <= TOL * abs(ref_l), (loss, ref_l)
+    assert rel_max(grad, ref_g) <= TOL and rel_l2(grad, ref_g) <= TOL, (rel_max(grad, ref_g), rel_l2(grad, ref_g))
+    # and no worse than the fp32 TF-faithful graph is
+    f32_g = golden[tag + "_dlogits_f32"]
+    assert rel_max(grad, ref_g) <= max(4 * rel_max(f32_g, ref_g), 2e-6)
+
+
+def _random_case(seed, V, n, K, B, T, mixed, dup=False, len_lo=1, scale=2.0):
+    rng = np.random.default_rng(seed)
+    ids, py = O.synth_table(V, n, K, seed=seed, min_id=0)
+    if mixed:
+        for z in range(K):
+            o = int(rng.integers(0 if z % 7 == 0 else 1, n + 1))
+            ids[z, o:] = -1
+    if dup:
+        ids[K // 2] = ids[0]
+        ids[K - 1] = ids[1]
+    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=len_lo, scale=scale)
+    if B > 2:
+        mask[0, :] = False
+    mask[-1, :] = True
+    return ids, py, logits, mask
+
+
+CASES = [
+    # seed, V, n, K, B, T, mixed, dup
+    (1, 9, 3, 40, 3, 9, False, False),
+    (2, 6, 4, 70, 2, 11, True, False),
+    (3, 5, 2, 20, 4, 5, True, True),
+    (4, 12, 1, 10, 2, 4, False, False),
+    (5, 7, 5, 300, 2, 8, True, True),
+    (6, 40, 3, 2000, 5, 131, False, False),      # crosses tile boundaries (tile = 128 rows)
+    (7, 48, 3, 10000, 6, 100, False, False),     # BASELINE configs[1] table size
+    (8, 40, 5, 1000, 9, 70, False, False),       # shipped TIMIT shape, ragged
+    (9, 13, 8, 500, 3, 40, True, True),          # maximum kernel size
+    (10, 33, 2, 700, 4, 257, True, False),       # V not a multiple of 4 (scalar staging path)
+    (11, 72, 5, 4000, 2, 300, True, False),      # LibriSpeech-shape phone inventory
+]
+
+
+@pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", CASES)
+def test_counts_fwd_bwd_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
+    ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px64 = O.softmax(logits)
+    px = torch.tensor(px64.astype(np.float32), device=dev)
+    px64 = px.cpu().numpy().astype(np.float64)           # the oracle sees exactly the fp32 posteriors the GPU sees
+    m = torch.tensor(mask, device=dev)
+    counts = eodm.counts_fwd(table, px, m).cpu().numpy()
+    S_ref, N_ref = O.counts_fwd(px64, mask, ids, n)
+    assert counts[K] == N_ref                             # integer count: exact
+    assert np.abs(counts[:K] - S_ref).max() <= TOL * np.abs(S_ref).max()
+    big = S_ref > 1e-30
+    assert (np.abs(counts[:K][big] - S_ref[big]) / S_ref[big]).max() <= TOL
+    gS = np.random.default_rng(seed).standard_normal(K).astype(np.float32)
+    dpx = eodm.counts_bwd(table, px, m, torch.tensor(gS, device=dev)).cpu().numpy()
+    d_ref = O.counts_bwd(px64, mask, ids, n, gS.astype(np.float64))
+    assert rel_max(dpx, d_ref) <= TOL and rel_l2(dpx, d_ref) <= TOL, (rel_max(dpx, d_ref), rel_l2(dpx, d_ref))
+    # padded frames of a fully masked utterance receive exactly zero
+    if B > 2:
+        assert not dpx[0].any()
+
+
+@pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", [CASES[1], CASES[5], CASES[7]])
+def test_eodm_loss_end_to_end_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
+    ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
+    loss, grad, _ = _loss_and_grad(eodm, ids, V, py, logits, mask, from_ids=True)
+    r = O.eodm_loss_direct(logits, mask, ids, n, py)
+    assert abs(loss - r["loss"]) <= TOL * abs(r["loss"])
+    assert rel_max(grad, r["dlogits"]) <= TOL and rel_l2(grad, r["dlogits"]) <= TOL
+
+
+def test_peaky_posteriors(eodm):
+    """logits x10: near one-hot posteriors; products underflow, eps terms matter."""
+    ids, py, logits, mask = _random_case(21, 48, 3, 3000, 4, 90, False, scale=20.0)
+    loss, grad, _ = _loss_and_grad(eodm, ids, 48, py, logits, mask, from_ids=True)
+    px32 = torch.softmax(torch.tensor(logits), -1).numpy()
+    S, N = O.counts_fwd(px32.astype(np.float64), mask, ids, 3)
+    ref_loss, gS = O.loss_from_counts(S, N, py)
+    assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss)
+    r = O.eodm_loss_direct(logits, mask, ids, 3, py)
+    assert rel_l2(grad, r["dlogits"]) <= 1e-4          # fp32 softmax of +-60 logits: looser, stated
+
+
+def test_materialising_op_and_vjp(eodm):
+    ids, py, logits, mask = _random_case(31, 11, 3, 50, 3, 12, True, True)
+    dev = _dev()
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, 11, device=0))
+    px64 = O.softmax(logits)
+    px = torch.tensor(px64.astype(np.float32), device=dev, requires_grad=True)
+    p = conv_op(px)
+    ref = next(O.window_products(px.detach().cpu().numpy().astype(np.float64), ids, 3, batch_chunk=3))[2]
+    assert tuple(p.shape) == ref.shape
+    assert rel_max(p.detach().cpu().numpy(), ref) <= TOL
+    w = torch.tensor(np.random.default_rng(0).standard_normal(ref.shape).astype(np.float32), device=dev)
+    (p * w).sum().backward()
+    # oracle: autograd of the literal log->conv->exp graph in fp64
+    pxt = torch.tensor(px.detach().cpu().numpy().astype(np.float64), requires_grad=True)
+    kern = torch.tensor(O.ids_to_kernel(ids, 11).astype(np.float64))
+    (O.p_ngram_literal(pxt, kern) * w.cpu().double()).sum().backward()
+    assert rel_max(px.grad.cpu().numpy(), pxt.grad.numpy()) <= TOL
+    # the literal reference expression built on the materialising op equals the fused loss
+    m = torch.tensor(mask, device=dev)
+    px2 = px.detach()
+    pz = conv_op(px2)
+    mk = m.float()[:, :, None]
+    lit = -(torch.tensor(py, device=dev) * torch.log((pz * mk[:, :pz.shape[1]]).sum((0, 1)) / mk.sum() + 1e-15)).sum()
+    fused = eodm.EODM_loss(torch.tensor(logits, device=dev), m, conv_op, 50, py)
+    assert abs(float(lit) - float(fused)) <= TOL * abs(float(fused))
+    conv_op.summary(print_fn=lambda s: None)
+
+
+def test_softmax_kernels(eodm):
+    dev = _dev()
+    x = torch.randn(37, 5, 48, device=dev) * 5
+    px = eodm.softmax_fwd(x)
+    assert torch.allclose(px, torch.softmax(x, -1), rtol=1e-6, atol=1e-9)
+    d = torch.randn_like(px)
+    ref = px * (d - (px * d).sum(-1, keepdim=True))
+    assert torch.allclose(eodm.softmax_bwd(px, d), ref, rtol=1e-5, atol=1e-7)
+
+
+def test_edge_cases_and_errors(eodm):
+    dev = _dev()
+    ids, py = O.synth_table(8, 3, 12, seed=0)
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, 8, device=0))
+    pyt = torch.tensor(py, device=dev)
+    # T == kernel_size: exactly one window per utterance
+    logits = np.random.default_rng(1).standard_normal((1, 3, 8)).astype(np.float32)
+    mask = np.ones((1, 3), bool)
+    loss = eodm.EODM_loss(torch.tensor(logits, device=dev), torch.tensor(mask, device=dev), conv_op, 12, pyt)
+    assert abs(float(loss) - O.eodm_loss_direct(logits, mask, ids, 3, py)["loss"]) <= TOL * abs(float(loss))
+    # window start valid but running into padding is still counted (EODM.py:19 tests the start only)
+    logits = np.random.default_rng(2).standard_normal((2, 6, 8)).astype(np.float32)
+    mask = np.array([[1, 1, 1, 1, 0, 0], [1, 0, 0, 0, 0, 0]], bool)
+    loss = eodm.EODM_loss(torch.tensor(logits, device=dev), torch.tensor(mask, device=dev), conv_op, 12, pyt)
+    assert abs(float(loss) - O.eodm_loss_direct(logits, mask, ids, 3, py)["loss"]) <= TOL * abs(float(loss))
+    # shapes the reference rejects
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.EODM_loss(torch.zeros(2, 2, 8, device=dev), torch.ones(2, 2, device=dev), conv_op, 12, pyt)   # T < n
+    assert e.value.status == -2
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.EODM_loss(torch.zeros(2, 5, 8, device=dev), torch.ones(2, 5, device=dev), conv_op, 12, pyt[:11])
+    assert e.value.status == -2
+    with pytest.raises(eodm.EodmError):
+        eodm.EODM_loss(torch.zeros(2, 5, 8), torch.ones(2, 5), conv_op, 12, pyt)       # CPU tensor: no CPU path
+    with pytest.raises(eodm.EodmError):
+        conv_op(torch.zeros(2, 2, 8, device=dev))
+
+
+def test_session_host_buffers(eodm):
+    ids, py, logits, mask = _random_case(41, 40, 5, 1000, 7, 60, False)
+    table = eodm.NgramTable.from_ids(ids, 40, device=0)
+    sess = eodm.Session(table, py, maxB=8, maxT=64)
+    dl = np.empty_like(logits)
+    loss = sess.loss(logits, mask, dl)
+    r = O.eodm_loss_direct(logits, mask, ids, 5, py)
+    assert abs(loss - r["loss"]) <= TOL * abs(r["loss"])
+    assert rel_max(dl, r["dlogits"]) <= TOL
+    assert sess.loss(logits, mask) == loss                     # forward only, same bits
+    with pytest.raises(eodm.EodmError):
+        sess.loss(np.zeros((9, 60, 40), np.float32), np.ones((9, 60), bool))   # larger than the session
+
+
+def test_full_size_properties(eodm):
+    """BASELINE configs[1] at full size (B=256, T=400, V=48, trigram top-10k):
+    size-independent checks -- closed form, determinism, linearity, homogeneity."""
+    from eodm_b200 import synth
+    dev = _dev()
+    w = synth.workload("timit_c2")
+    B, T, V, n, K = w["B"], w["T"], w["V"], w["n"], w["K"]
+    table = eodm.NgramTable.from_ids(w["ids"], V, device=0)
+    m = torch.tensor(w["mask"], device=dev)
+    # closed form: uniform posterior -> S[z] = B (T-n+1) (1/V + eps)^n, N = B T
+    px_u = torch.full((B, T, V), 1.0 / V, device=dev)
+    c = eodm.counts_fwd(table, px_u, m).cpu().numpy().astype(np.float64)
+    want = B * (T - n + 1) * (np.float64(np.float32(1.0 / V)) + 1e-15) ** n
+    assert c[K] == B * T
+    assert np.abs(c[:K] / want - 1).max() <= TOL
+    # random posteriors
+    px = eodm.softmax_fwd(torch.tensor(w["logits"], device=dev))
+    c1 = eodm.counts_fwd(table, px, m)
+    c2 = eodm.counts_fwd(table, px, m)
+    assert torch.equal(c1, c2)                                  # deterministic: bit-identical reruns
+    g1 = torch.randn(K, device=dev)
+    g2 = torch.randn(K, device=dev)
+    d1 = eodm.counts_bwd(table, px, m, g1)
+    d2 = eodm.counts_bwd(table, px, m, g2)
+    d12 = eodm.counts_bwd(table, px, m, g1 + 2 * g2)
+    assert torch.equal(d1, eodm.counts_bwd(table, px, m, g1))
+    assert float((d12 - (d1 + 2 * d2)).abs().max()) <= 1e-5 * float(d12.abs().max())     # linear in gS
+    # Euler: S is homogeneous of degree n in (px + eps):  sum (px+eps) * dpx = n * sum gS * S
+    lhs = float(((px.double() + 1e-15) * d1.double()).sum())
+    rhs = float(n * (g1.double() * c1[:K].double()).sum())
+    scale = n * float((g1.double().abs() * c1[:K].double()).sum())
+    assert abs(lhs - rhs) <= 2e-6 * scale
+    # sampled n-grams against a direct fp64 evaluation on the host
+    pxh = px.cpu().numpy().astype(np.float64) + 1e-15
+    for z in (0, 17, 4999, 9999):
+        a, b_, cc = w["ids"][z]
+        s = (pxh[:, :T - 2, a] * pxh[:, 1:T - 1, b_] * pxh[:, 2:, cc]).sum()
+        assert abs(float(c1[z]) - s) <= TOL * s
+    # sampled rows of the gradient against the oracle restricted to one utterance (windows do not cross utterances)
+    d_ref = O.counts_bwd(pxh[3:4] - 1e-15, w["mask"][3:4], w["ids"], n, g1.cpu().numpy().astype(np.float64))
+    assert rel_max(d1[3:4].cpu().numpy(), d_ref) <= TOL

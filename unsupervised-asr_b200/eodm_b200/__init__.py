@@ -8,4 +8,4 @@ from .tools import load_vocab, read_ngram, ngram2kernel, ngram_ids  # noqa: F401
 from .EODM import (P_Ngram, EODM_loss, PNgram, NgramTable, softmax_fwd, softmax_bwd, counts_fwd, counts_bwd,  # noqa: F401
                    loss_from_counts)
 from .session import Session  # noqa: F401
-from . import dist  # noqa: F401
+from . import dist, synth  # noqa: F401
