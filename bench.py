@@ -299,7 +299,7 @@ def main():
                "sample": r["sample"] + "; 1 warm-up + best of 3 (%.2f s)" % best}
 
     if rank == 0:
-        launches_per_step = 6 + n   # softmax, counts fwd, finish, loss, n x permute_g, counts bwd, softmax VJP
+        launches_per_step = 7       # softmax, counts fwd, finish, loss, prepare_g, counts bwd, softmax VJP
         out = {
             "metric": "EODM fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -307,7 +307,7 @@ def main():
             "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
                        "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
-                       "path": "cuda-core trie walk"},
+                       "path": "cuda-core trie walk (v1)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }

@@ -111,6 +111,34 @@ def test_counts_fwd_bwd_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
         assert not dpx[0].any()
 
 
+@pytest.mark.parametrize("case", [5, 6, 7, 8, 10])
+def test_every_tile_variant(eodm, case):
+    """Every compiled windows-per-lane variant (R = 1, 4, 8, 12) and odd tile heights, pinned through the
+    debug hook, against the same oracle result."""
+    from eodm_b200._lib import lib
+    seed, V, n, K, B, T, mixed, dup = CASES[case]
+    ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    px64 = px.cpu().numpy().astype(np.float64)
+    m = torch.tensor(mask, device=dev)
+    S_ref, N_ref = O.counts_fwd(px64, mask, ids, n)
+    gS = np.random.default_rng(seed).standard_normal(K).astype(np.float32)
+    d_ref = O.counts_bwd(px64, mask, ids, n, gS.astype(np.float64))
+    gSt = torch.tensor(gS, device=dev)
+    try:
+        for R, ts in [(1, 0), (1, 29), (4, 0), (4, 101), (8, 0), (8, 250), (12, 0), (12, 383), (12, 321)]:
+            lib.eodm_debug_set_tiling(R, ts)
+            counts = eodm.counts_fwd(table, px, m).cpu().numpy()
+            assert counts[K] == N_ref, (R, ts)
+            assert np.abs(counts[:K] - S_ref).max() <= TOL * np.abs(S_ref).max(), (R, ts)
+            dpx = eodm.counts_bwd(table, px, m, gSt).cpu().numpy()
+            assert rel_max(dpx, d_ref) <= TOL and rel_l2(dpx, d_ref) <= TOL, (R, ts, rel_max(dpx, d_ref))
+    finally:
+        lib.eodm_debug_set_tiling(0, 0)
+
+
 @pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", [CASES[1], CASES[5], CASES[7]])
 def test_eodm_loss_end_to_end_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
     ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)

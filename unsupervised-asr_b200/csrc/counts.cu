@@ -9,20 +9,26 @@
 // Layout.  px f32[B][T][V] is viewed as NR = B*T rows of V floats; a window is
 // named by the row it starts at and is valid iff mask[row] and t <= T - n.  A
 // window never reads past its own utterance when valid, so tiles are cut from
-// the flat row space without regard to utterance boundaries.
+// the flat row space without regard to utterance boundaries; the tile height
+// is chosen on the host so that the tiles divide evenly over the SMs.
 //
-// A CTA stages a tile of rows transposed into shared memory, Ps[v][row] (row
-// stride odd => the transposing stores are conflict-free, and a warp reading 32
-// consecutive rows of one phone is one wavefront).  Lanes own windows (R per
-// lane); every warp owns a fixed share of the trie and walks it depth-first
-// with the running products in registers, one register set per level.
+// A CTA (one per SM, 16 warps) stages a tile of rows transposed into shared
+// memory, Ps[v][row] (row stride odd => the transposing stores are conflict-free,
+// and a warp reading 32 consecutive rows of one phone is one wavefront).  Lanes
+// own windows (R per lane); every warp owns a fixed share of the trie and walks
+// it depth-first with the running products in registers, one set per level.
+// The walk is bound by shared-memory wavefronts: one per 32 (node, window) pairs.
 //
-// Forward: per n-gram the tile sum is formed by shuffles and accumulated by the
-// owning warp in shared memory; after its last tile the CTA writes its partial
-// vector, and eodm_counts_finish_kernel adds the CTA partials in a fixed order.
+// Forward: per n-gram the lanes' partial sums are parked in a per-warp staging
+// tile and summed 16 n-grams at a time (one LDS column per lane instead of a
+// shuffle tree per n-gram), accumulated by the owning warp in shared memory;
+// after its last tile the CTA writes its partial vector, and
+// eodm_counts_finish_kernel adds the CTA partials in a fixed order.
 // Backward: gather form.  Trie j is rooted at window position j, so the walk of
 // the subtree below root phone v yields d/dpx[row][v] for the lane's own row --
-// no scatter, no atomics.  Results are bit-reproducible run to run.
+// no scatter, no atomics.  dloss/dS is interleaved with the node stream
+// beforehand so that a node and its gradient arrive in one 64-bit load.
+// Results are bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,11 +41,14 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr float kEps = 1e-15f;  // models/EODM.py:63
+constexpr int kStageLeaves = 16;
+constexpr int kStageLd = 33;
 
 struct TrieArg {
-  const uint32_t* nodes;
+  const uint32_t* nodes;  // forward: node words
+  const uint2* ng;        // backward: (node word, dloss/dS of the n-gram ending there or 0)
   const EodmUnit* units;
-  const float* g;  // backward: dloss/dS in this trie's leaf order
+  const float* g;         // backward: dloss/dS in this trie's leaf order (for n-grams ending at the root)
   int n_units;
   uint32_t total_cost;
   int off[EODM_MAX_N];  // level -> column offset inside the staged tile
@@ -50,29 +59,6 @@ struct BwdArgs {
 };
 
 __host__ __device__ inline int odd_ld(int x) { return x | 1; }
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Sequential reader of a trie's pre-order node stream with a one-word lookahead.
-struct Walk {
-  const uint32_t* nodes;
-  uint32_t cursor, ahead, leaf;
-  __device__ __forceinline__ void seek(uint32_t c, uint32_t l) {
-    cursor = c;
-    leaf = l;
-    ahead = __ldg(nodes + c);
-  }
-  __device__ __forceinline__ uint32_t next() {
-    uint32_t e = ahead;
-    ++cursor;
-    ahead = __ldg(nodes + cursor);  // the stream is allocated with one word of slack
-    return e;
-  }
-};
 
 // first unit whose cost prefix reaches `target`
 __device__ __forceinline__ int unit_lower_bound(const EodmUnit* units, int n, uint32_t target) {
@@ -92,10 +78,12 @@ __device__ __forceinline__ void warp_unit_range(const TrieArg& tr, int warp, int
   hi = (warp + 1 == kWarps) ? tr.n_units : unit_lower_bound(tr.units, tr.n_units, t1);
 }
 
-// Stage rows [row0, row0 + nrows) of px, plus eps, transposed into Ps[v][ld].
-// Rows outside [0, NR) are staged as zero (their windows are masked anyway).
+// Stage rows [row0, row0 + nrows) of px, plus eps, transposed into Ps[v][ld]; columns nrows .. ncols-1 and
+// rows outside [0, NR) are staged as zero: their windows are masked, but 0 * garbage must stay 0.
 __device__ __forceinline__ void stage_tile(float* Ps, int ld, const float* __restrict__ px, long long row0, int nrows,
-                                           long long NR, int V) {
+                                           int ncols, long long NR, int V) {
+  NR = (row0 + nrows < NR) ? row0 + nrows : NR;
+  nrows = ncols;
   if ((V & 3) == 0) {
     const int V4 = V >> 2;
     const int total = nrows * V4;
@@ -131,13 +119,54 @@ __device__ __forceinline__ float window_valid(const uint8_t* __restrict__ mask, 
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
+struct FwdWalk {
+  const uint32_t* nodes;
+  uint32_t cursor, ahead;
+  float* stage;     // this warp's [kStageLeaves][kStageLd] staging tile
+  float* acc;       // per-CTA accumulators, leaf order
+  uint32_t leaf0;   // leaf index of stage row 0
+  int pend;         // rows of `stage` in use
+  int lane;
+  __device__ __forceinline__ void seek(uint32_t c) {
+    cursor = c;
+    ahead = __ldg(nodes + c);
+  }
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t e = ahead;
+    ++cursor;
+    ahead = __ldg(nodes + cursor);  // every trie's stream is followed by one word of slack
+    return e;
+  }
+  // sum the parked partials: lane l adds half (l >> 4) of row (l & 15); rows are padded to 33 words so the
+  // 32 lanes read 32 distinct banks
+  __device__ __forceinline__ void flush() {
+    __syncwarp();
+    const int row = lane & (kStageLeaves - 1), half = lane >> 4;
+    float v = 0.f;
+    if (row < pend) {
+      const float* s = stage + row * kStageLd + half * 16;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v += s[k];
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < pend) acc[leaf0 + lane] += v;
+    leaf0 += pend;
+    pend = 0;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void emit(float s) {
+    stage[pend * kStageLd + lane] = s;
+    if (++pend == kStageLeaves) flush();
+  }
+};
+
 template <int L, int DEPTH, int R>
-__device__ __forceinline__ void fwd_visit(Walk& w, const TrieArg& tr, const float* Ps, int ld, int lane,
-                                          const float (&qp)[R], int count, float* acc) {
+__device__ __forceinline__ void fwd_visit(FwdWalk& w, const TrieArg& tr, const float* Pl, int ld, const float (&qp)[R],
+                                          int count) {
 #pragma unroll 1
   for (int c = 0; c < count; ++c) {
     const uint32_t e = w.next();
-    const float* row = Ps + EODM_NODE_PHONE(e) * ld + tr.off[L] + lane;
+    const float* row = Pl + EODM_NODE_PHONE(e) * ld + tr.off[L];
     float q[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) q[r] = qp[r] * row[32 * r];
@@ -145,51 +174,56 @@ __device__ __forceinline__ void fwd_visit(Walk& w, const TrieArg& tr, const floa
       float s = q[0];
 #pragma unroll
       for (int r = 1; r < R; ++r) s += q[r];
-      s = warp_sum(s);
-      if (lane == 0) acc[w.leaf] += s;
-      ++w.leaf;
+      w.emit(s);
     }
     if constexpr (L + 1 < DEPTH) {
       const int nc = EODM_NODE_NCHILD(e);
-      if (nc) fwd_visit<L + 1, DEPTH, R>(w, tr, Ps, ld, lane, q, nc, acc);
+      if (nc) fwd_visit<L + 1, DEPTH, R>(w, tr, Pl, ld, q, nc);
     }
   }
 }
 
-template <int DEPTH, int R>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int DEPTH, int R, bool ACC_SMEM>
+__global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restrict__ px,
-                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int n_tiles,
+                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int n_tiles,
                        int n_leaves, float* __restrict__ part, int* __restrict__ part_cnt) {
   constexpr int TS = 32 * R;
   extern __shared__ float smem[];
   const int ld = odd_ld(TS + n - 1);
-  float* Ps = smem;              // [V][ld]
-  float* wm = Ps + V * ld;       // [TS]
-  float* acc = wm + TS;          // [n_leaves]
+  float* Ps = smem;                                   // [V][ld]
+  float* wm = Ps + V * ld;                            // [TS]
+  float* stage = wm + TS;                             // [kWarps][kStageLeaves][kStageLd]
+  float* acc_s = stage + kWarps * kStageLeaves * kStageLd;  // [n_leaves] when ACC_SMEM
   __shared__ int s_cnt[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* acc = ACC_SMEM ? acc_s : part + (size_t)blockIdx.x * n_leaves;
 
   for (int i = threadIdx.x; i < n_leaves; i += kThreads) acc[i] = 0.f;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   int u_lo, u_hi;
   warp_unit_range(tr, warp, u_lo, u_hi);
-  Walk w;
+  FwdWalk w;
   w.nodes = tr.nodes;
+  w.stage = stage + warp * kStageLeaves * kStageLd;
+  w.acc = acc;
+  w.lane = lane;
+  const float* Pl = Ps + lane;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = (long long)tile * TS;
+    const long long row0 = (long long)tile * ts;
     __syncthreads();  // the previous tile is fully consumed (and acc / s_cnt are initialised)
-    stage_tile(Ps, ld, px, row0, TS + n - 1, NR, V);
+    stage_tile(Ps, ld, px, row0, ts + n - 1, TS + n - 1, NR, V);
     int my_valid = 0;
-    if (threadIdx.x < TS) {
-      long long row = row0 + threadIdx.x;
-      float ok = window_valid(mask, row, NR, T, n);
-      wm[threadIdx.x] = ok;
-      my_valid = ok != 0.f;
-      int in_mask = (row < NR && __ldg(mask + row) != 0);
+    for (int i = threadIdx.x; i < TS; i += kThreads) {   // warp-uniform trip count: TS is a multiple of 32
+      const long long row = row0 + i;
+      const bool in_tile = i < ts && row < NR;
+      const float ok = in_tile ? window_valid(mask, row, NR, T, n) : 0.f;
+      wm[i] = ok;
+      my_valid |= ok != 0.f;
+      const int in_mask = in_tile && __ldg(mask + row) != 0;
       // N counts every valid frame (EODM.py:20), the order-0 columns count valid windows
-      unsigned bm = __ballot_sync(0xffffffffu, in_mask), bw = __ballot_sync(0xffffffffu, my_valid);
+      const unsigned bm = __ballot_sync(0xffffffffu, in_mask), bw = __ballot_sync(0xffffffffu, ok != 0.f);
       if (lane == 0) {
         if (bm) atomicAdd(&s_cnt[0], __popc(bm));
         if (bw) atomicAdd(&s_cnt[1], __popc(bw));
@@ -202,12 +236,14 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
     for (int r = 0; r < R; ++r) wmv[r] = wm[lane + 32 * r];
     int prev_root = -1;
     float q0[R];
+    w.pend = 0;
 #pragma unroll 1
     for (int u = u_lo; u < u_hi; ++u) {
       const uint4 un = __ldg(reinterpret_cast<const uint4*>(tr.units) + u);
       const int root = un.z & 0xffff;
+      if (u == u_lo) w.leaf0 = un.y;
       if (root != prev_root) {
-        const float* row = Ps + root * ld + tr.off[0] + lane;
+        const float* row = Pl + root * ld + tr.off[0];
 #pragma unroll
         for (int r = 0; r < R; ++r) q0[r] = row[32 * r] * wmv[r];
         prev_root = root;
@@ -216,31 +252,41 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
         float s = q0[0];
 #pragma unroll
         for (int r = 1; r < R; ++r) s += q0[r];
-        s = warp_sum(s);
-        if (lane == 0) acc[un.y] += s;
+        w.emit(s);
       } else if constexpr (DEPTH > 1) {
-        w.seek(un.x, un.y);
-        fwd_visit<1, DEPTH, R>(w, tr, Ps, ld, lane, q0, 1, acc);
+        w.seek(un.x);
+        fwd_visit<1, DEPTH, R>(w, tr, Pl, ld, q0, 1);
       }
     }
+    if (w.pend) w.flush();
   }
   __syncthreads();
-  float* out = part + (size_t)blockIdx.x * n_leaves;
-  for (int i = threadIdx.x; i < n_leaves; i += kThreads) out[i] = acc[i];
+  if (ACC_SMEM) {
+    float* out = part + (size_t)blockIdx.x * n_leaves;
+    for (int i = threadIdx.x; i < n_leaves; i += kThreads) out[i] = acc[i];
+  }
   if (threadIdx.x < 2) part_cnt[blockIdx.x * 2 + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
 // S[perm[leaf]] = sum over CTAs (fixed order) of part[cta][leaf]; order-0 n-grams get the
 // number of valid windows; N = number of valid frames.
-__global__ void eodm_counts_finish_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int n_cta,
-                                          int n_leaves, const int32_t* __restrict__ perm,
-                                          const int32_t* __restrict__ order0, int n_order0, float* __restrict__ S,
-                                          float* __restrict__ N) {
+__global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __restrict__ part,
+                                                                 const int* __restrict__ part_cnt, int n_cta,
+                                                                 int n_leaves, const int32_t* __restrict__ perm,
+                                                                 const int32_t* __restrict__ order0, int n_order0,
+                                                                 float* __restrict__ S, float* __restrict__ N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_leaves) {
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += part[(size_t)c * n_leaves + i];
-    S[perm[i]] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains; the order is fixed
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+      s0 += part[(size_t)c * n_leaves + i];
+      s1 += part[(size_t)(c + 1) * n_leaves + i];
+      s2 += part[(size_t)(c + 2) * n_leaves + i];
+      s3 += part[(size_t)(c + 3) * n_leaves + i];
+    }
+    for (; c < n_cta; ++c) s0 += part[(size_t)c * n_leaves + i];
+    S[perm[i]] = (s0 + s1) + (s2 + s3);
   }
   if (i < n_order0 || i == 0) {
     long long cn = 0, cw = 0;
@@ -256,55 +302,74 @@ __global__ void eodm_counts_finish_kernel(const float* __restrict__ part, const 
 // ---------------------------------------------------------------------------
 // backward (gather form)
 // ---------------------------------------------------------------------------
+struct BwdWalk {
+  const uint2* ng;
+  uint32_t cursor;
+  uint2 ahead;
+  __device__ __forceinline__ void seek(uint32_t c) {
+    cursor = c;
+    ahead = __ldg(ng + c);
+  }
+  __device__ __forceinline__ uint2 next() {
+    uint2 e = ahead;
+    ++cursor;
+    ahead = __ldg(ng + cursor);
+    return e;
+  }
+};
+
 template <int L, int DEPTH, int R>
-__device__ __forceinline__ void bwd_visit(Walk& w, const TrieArg& tr, const float* Ps, int ld, int lane,
-                                          float (&out)[R], int count) {
+__device__ __forceinline__ void bwd_visit(BwdWalk& w, const TrieArg& tr, const float* Pl, int ld, float (&out)[R],
+                                          int count) {
 #pragma unroll 1
   for (int c = 0; c < count; ++c) {
-    const uint32_t e = w.next();
-    float s[R];
-    float g = 0.f;
-    if (EODM_NODE_HASZ(e)) {
-      g = __ldg(tr.g + w.leaf);
-      ++w.leaf;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) s[r] = g;
+    const uint2 e = w.next();
+    const float g = __uint_as_float(e.y);  // 0 unless an n-gram ends here
+    const float* row = Pl + EODM_NODE_PHONE(e.x) * ld + tr.off[L];
     if constexpr (L + 1 < DEPTH) {
-      const int nc = EODM_NODE_NCHILD(e);
-      if (nc) bwd_visit<L + 1, DEPTH, R>(w, tr, Ps, ld, lane, s, nc);
-    }
-    const float* row = Ps + EODM_NODE_PHONE(e) * ld + tr.off[L] + lane;
+      const int nc = EODM_NODE_NCHILD(e.x);
+      if (nc) {
+        float s[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], s[r], out[r]);
+        for (int r = 0; r < R; ++r) s[r] = g;
+        bwd_visit<L + 1, DEPTH, R>(w, tr, Pl, ld, s, nc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], s[r], out[r]);
+        continue;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, out[r]);
   }
 }
 
 template <int DEPTH, int R>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __restrict__ px,
-                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int n_tiles,
+                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int n_tiles,
                        float* __restrict__ dpx) {
   constexpr int TS = 32 * R;
   extern __shared__ float smem[];
   const int ld = odd_ld(TS + 2 * (n - 1));
   const int ldo = odd_ld(TS);
-  float* Ps = smem;                       // [V][ld]   rows row0-(n-1) .. row0+TS+n-2
+  float* Ps = smem;                       // [V][ld]   rows row0-(n-1) .. row0+ts+n-2
   float* dP = Ps + V * ld;                // [V][ldo]
   float* wm = dP + V * ldo;               // [TS+n-1]  windows row0-(n-1) .. row0+TS-1
   float* side = wm + (TS + n - 1);        // [kWarps][2][TS]
   __shared__ int side_root[kWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Walk w;
+  const float* Pl = Ps + lane;
+  BwdWalk w;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = (long long)tile * TS;
+    const long long row0 = (long long)tile * ts;
     __syncthreads();
-    stage_tile(Ps, ld, px, row0 - (n - 1), TS + 2 * (n - 1), NR, V);
+    stage_tile(Ps, ld, px, row0 - (n - 1), ts + 2 * (n - 1), TS + 2 * (n - 1), NR, V);
     for (int i = threadIdx.x; i < V * ldo; i += kThreads) dP[i] = 0.f;
     int my_valid = 0;
     for (int i = threadIdx.x; i < TS + n - 1; i += kThreads) {
-      float ok = window_valid(mask, row0 - (n - 1) + i, NR, T, n);
+      // window i starts at row row0-(n-1)+i; it feeds output rows of this tile only if it starts before row0+ts
+      const float ok = (i < ts + n - 1) ? window_valid(mask, row0 - (n - 1) + i, NR, T, n) : 0.f;
       wm[i] = ok;
       my_valid |= ok != 0.f;
     }
@@ -312,7 +377,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const TrieArg& tr = args.trie[j];
-        w.nodes = tr.nodes;
+        w.ng = tr.ng;
         int u_lo, u_hi;
         warp_unit_range(tr, warp, u_lo, u_hi);
         if (lane < 2) side_root[warp][lane] = -1;
@@ -353,8 +418,8 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] += g;
           } else if constexpr (DEPTH > 1) {
-            w.seek(un.x, un.y);
-            bwd_visit<1, DEPTH, R>(w, tr, Ps, ld, lane, acc, 1);
+            w.seek(un.x);
+            bwd_visit<1, DEPTH, R>(w, tr, Pl, ld, acc, 1);
           }
         }
         if (cur_root >= 0) {
@@ -374,9 +439,9 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
         __syncthreads();
       }
     }
-    // write the tile: rows row0 .. row0+TS-1, V floats each, contiguous in dpx
+    // write the tile: rows row0 .. row0+ts-1, V floats each, contiguous in dpx
     {
-      const int total = TS * V;
+      const int total = ts * V;
       for (int idx = threadIdx.x; idx < total; idx += kThreads) {
         int r = idx / V, v = idx - r * V;
         long long gr = row0 + r;
@@ -386,16 +451,26 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
   }
 }
 
-// g in each trie's leaf order
-__global__ void eodm_permute_g_kernel(const float* __restrict__ gS, const int32_t* __restrict__ perm, int n_leaves,
-                                      float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_leaves) out[i] = gS[perm[i]];
+// dloss/dS interleaved with every trie's node stream, and in every trie's leaf order
+__global__ void __launch_bounds__(256) eodm_prepare_g_kernel(const float* __restrict__ gS,
+                                                             const uint32_t* __restrict__ nodes,
+                                                             const int32_t* __restrict__ node_z, long long n_nodes,
+                                                             const int32_t* __restrict__ perm, long long n_leaves,
+                                                             uint2* __restrict__ ng, float* __restrict__ gperm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes) {
+    const int z = node_z[i];
+    ng[i] = make_uint2(nodes[i], z >= 0 ? __float_as_uint(gS[z]) : 0u);
+  }
+  if (i < n_leaves) gperm[i] = gS[perm[i]];
 }
 
-size_t fwd_smem_bytes(int R, int V, int n, int n_leaves) {
+constexpr int kMaxSmem = 227 * 1024;
+
+size_t fwd_smem_bytes(int R, int V, int n, int n_leaves, bool acc_smem) {
   const int TS = 32 * R;
-  return sizeof(float) * ((size_t)V * odd_ld(TS + n - 1) + TS + n_leaves);
+  return sizeof(float) * ((size_t)V * odd_ld(TS + n - 1) + TS + (size_t)kWarps * kStageLeaves * kStageLd +
+                          (acc_smem ? n_leaves : 0));
 }
 size_t bwd_smem_bytes(int R, int V, int n) {
   const int TS = 32 * R;
@@ -403,104 +478,169 @@ size_t bwd_smem_bytes(int R, int V, int n) {
                           (size_t)kWarps * 2 * TS);
 }
 
-constexpr int kMaxSmem = 227 * 1024;
-constexpr int kR = 4;  // windows per lane
+// windows-per-lane variants compiled for a given trie depth (register budget: R floats per level)
+constexpr int kRs[] = {12, 8, 4, 1};
+__host__ inline bool r_allowed(int depth, int R) { return R <= 8 || depth <= 5; }
 
-template <int DEPTH>
-cudaError_t launch_fwd(const TrieArg& tr, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
-                       int n_tiles, int n_leaves, float* part, int* part_cnt, int grid, size_t smem, cudaStream_t st) {
-  auto k = eodm_counts_fwd_kernel<DEPTH, kR>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, n_tiles, n_leaves, part, part_cnt);
-  return cudaGetLastError();
+// Tile height: the smallest number of equal row slices per SM such that a slice fits the lanes.
+struct Tiling {
+  int R, ts, n_tiles, grid;
+};
+int g_force_R = 0, g_force_ts = 0;  // test hook (eodm_debug_set_tiling): 0 = choose automatically
+constexpr int kMinTileRows = 128;   // a tile costs a full trie walk whatever its height: do not cut finer
+
+template <typename FitFn>
+bool choose_tiling(const eodm_table* t, long long NR, FitFn fits, Tiling* out) {
+  int Rmax = 0;
+  for (int R : kRs)
+    if (r_allowed(t->n, R) && fits(R) && (!g_force_R || R <= g_force_R)) {
+      Rmax = R;
+      break;
+    }
+  if (!Rmax) return false;
+  const long long sms = t->sm_count;
+  long long ts = 0;
+  for (long long k = 1;; ++k) {
+    ts = (NR + sms * k - 1) / (sms * k);
+    if (ts <= 32LL * Rmax) break;
+  }
+  if (ts < kMinTileRows) ts = kMinTileRows < 32LL * Rmax ? kMinTileRows : 32LL * Rmax;
+  if (ts > NR) ts = NR;
+  if (g_force_ts > 0 && g_force_ts <= 32 * Rmax) ts = g_force_ts;
+  if (ts < 1) ts = 1;
+  int R = Rmax;
+  for (int cand : kRs)
+    if (cand <= Rmax && 32LL * cand >= ts) R = cand;  // smallest compiled R that still covers ts
+  if (g_force_R && g_force_R <= Rmax) R = g_force_R;
+  const long long n_tiles = (NR + ts - 1) / ts;
+  out->R = R;
+  out->ts = (int)ts;
+  out->n_tiles = (int)n_tiles;
+  out->grid = (int)(n_tiles < sms ? n_tiles : sms);
+  return n_tiles <= 0x7fffffffLL;
 }
 
-template <int DEPTH>
-cudaError_t launch_bwd(const BwdArgs& a, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
-                       int n_tiles, float* dpx, int grid, size_t smem, cudaStream_t st) {
-  auto k = eodm_counts_bwd_kernel<DEPTH, kR>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, n_tiles, dpx);
-  return cudaGetLastError();
+template <int DEPTH, int R>
+cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
+                          const Tiling& tl, int n_leaves, bool acc_smem, float* part, int* part_cnt, size_t smem,
+                          cudaStream_t st) {
+  if constexpr (!(R <= 8 || DEPTH <= 5)) {
+    return cudaErrorInvalidValue;
+  } else {
+    cudaError_t e;
+    if (acc_smem) {
+      auto k = eodm_counts_fwd_kernel<DEPTH, R, true>;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, n_leaves, part, part_cnt);
+    } else {
+      auto k = eodm_counts_fwd_kernel<DEPTH, R, false>;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, n_leaves, part, part_cnt);
+    }
+    return cudaGetLastError();
+  }
 }
 
-#define EODM_DISPATCH_DEPTH(n, CALL)                  \
+template <int DEPTH, int R>
+cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
+                          const Tiling& tl, float* dpx, size_t smem, cudaStream_t st) {
+  if constexpr (!(R <= 8 || DEPTH <= 5)) {
+    return cudaErrorInvalidValue;
+  } else {
+    auto k = eodm_counts_bwd_kernel<DEPTH, R>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, dpx);
+    return cudaGetLastError();
+  }
+}
+
+#define EODM_DISPATCH_R(D, R, CALL)                   \
+  switch (R) {                                        \
+    case 12: e = CALL(D, 12); break;                  \
+    case 8: e = CALL(D, 8); break;                    \
+    case 4: e = CALL(D, 4); break;                    \
+    default: e = CALL(D, 1); break;                   \
+  }
+// trie depths 6 and 7 run the depth-8 instantiation (the walk stops where the trie does)
+#define EODM_DISPATCH(n, R, CALL)                     \
   switch (n) {                                        \
-    case 1: e = CALL(1); break;                       \
-    case 2: e = CALL(2); break;                       \
-    case 3: e = CALL(3); break;                       \
-    case 4: e = CALL(4); break;                       \
-    case 5: e = CALL(5); break;                       \
-    case 6: e = CALL(6); break;                       \
-    case 7: e = CALL(7); break;                       \
-    default: e = CALL(8); break;                      \
+    case 1: EODM_DISPATCH_R(1, R, CALL) break;        \
+    case 2: EODM_DISPATCH_R(2, R, CALL) break;        \
+    case 3: EODM_DISPATCH_R(3, R, CALL) break;        \
+    case 4: EODM_DISPATCH_R(4, R, CALL) break;        \
+    case 5: EODM_DISPATCH_R(5, R, CALL) break;        \
+    default: EODM_DISPATCH_R(8, R, CALL) break;       \
   }
 
-int grid_for(const eodm_table* t, int n_tiles, size_t smem) {
-  int per_sm = (smem * 2 + 2048 <= (size_t)kMaxSmem) ? 2 : 1;
-  int g = t->sm_count * per_sm;
-  return n_tiles < g ? n_tiles : g;
-}
+size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------
 // host entry points (called from the C ABI in api.cc)
 // ---------------------------------------------------------------------------
-// workspace layout: [part: kMaxGrid x n_leaves0 f32][part_cnt: kMaxGrid x 2 i32][g: total_leaves f32]
-static int max_grid(const eodm_table* t) { return 2 * t->sm_count; }
-
-size_t eodm_counts_workspace_bytes(const eodm_table* t) {
-  size_t part = (size_t)max_grid(t) * (size_t)t->trie[0].n_leaves * sizeof(float);
-  size_t cnt = (size_t)max_grid(t) * 2 * sizeof(int);
-  size_t g = (size_t)t->total_leaves * sizeof(float);
-  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  return up(part) + up(cnt) + up(g) + 256;
+// Test hook, not part of the public header: pin the windows-per-lane variant (1, 4, 8, 12) and the tile
+// height so that the parity tests can drive every compiled variant at small sizes.  (0, 0) restores the default.
+extern "C" void eodm_debug_set_tiling(int R, int ts) {
+  g_force_R = R;
+  g_force_ts = ts;
 }
 
-static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, float** g) {
-  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+// workspace: [part: sm_count x n_leaves0 f32][part_cnt: sm_count x 2 i32][gperm: total_leaves f32]
+//            [ng: total_nodes_padded x (u32, f32)]
+size_t eodm_counts_workspace_bytes(const eodm_table* t) {
+  return up256((size_t)t->sm_count * (size_t)t->trie[0].n_leaves * sizeof(float)) +
+         up256((size_t)t->sm_count * 2 * sizeof(int)) + up256((size_t)t->total_leaves * sizeof(float)) +
+         up256((size_t)t->total_nodes_padded * sizeof(uint2)) + 256;
+}
+
+static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, float** g, uint2** ng) {
   char* p = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   *part = (float*)p;
-  p += up((size_t)max_grid(t) * (size_t)t->trie[0].n_leaves * sizeof(float));
+  p += up256((size_t)t->sm_count * (size_t)t->trie[0].n_leaves * sizeof(float));
   *cnt = (int*)p;
-  p += up((size_t)max_grid(t) * 2 * sizeof(int));
+  p += up256((size_t)t->sm_count * 2 * sizeof(int));
   *g = (float*)p;
+  p += up256((size_t)t->total_leaves * sizeof(float));
+  *ng = (uint2*)p;
 }
 
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
                            void* ws, cudaStream_t st) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
-  const int TS = 32 * kR;
-  const long long n_tiles_ll = (NR + TS - 1) / TS;
-  if (n_tiles_ll > 0x7fffffff) {
-    eodm_set_error("B*T too large");
-    return EODM_EUNSUPPORTED;
-  }
-  const int n_tiles = (int)n_tiles_ll;
   const int n_leaves = t->trie[0].n_leaves;
-  const size_t smem = fwd_smem_bytes(kR, V, n, n_leaves);
-  if (smem > (size_t)kMaxSmem) {
-    eodm_set_error("trie path needs %zu bytes of shared memory (V=%d, K=%d) > %d", smem, V, t->K, kMaxSmem);
-    return EODM_EUNSUPPORTED;
+  bool acc_smem = true;
+  Tiling tl;
+  auto fits_s = [&](int R) { return fwd_smem_bytes(R, V, n, n_leaves, true) <= (size_t)kMaxSmem; };
+  auto fits_g = [&](int R) { return fwd_smem_bytes(R, V, n, n_leaves, false) <= (size_t)kMaxSmem; };
+  // prefer shared-memory accumulators unless they force a much smaller tile than global ones would allow
+  if (!choose_tiling(t, NR, fits_s, &tl)) {
+    acc_smem = false;
+    if (!choose_tiling(t, NR, fits_g, &tl)) {
+      eodm_set_error("trie path: a [V=%d] x 32-row tile does not fit in %d bytes of shared memory", V, kMaxSmem);
+      return EODM_EUNSUPPORTED;
+    }
   }
+  const size_t smem = fwd_smem_bytes(tl.R, V, n, n_leaves, acc_smem);
   float *part, *g;
   int* cnt;
-  ws_carve(t, ws, &part, &cnt, &g);
+  uint2* ng;
+  ws_carve(t, ws, &part, &cnt, &g, &ng);
   TrieArg tr;
   tr.nodes = t->trie[0].nodes;
+  tr.ng = nullptr;
   tr.units = t->trie[0].units;
   tr.g = nullptr;
   tr.n_units = t->trie[0].n_units;
   tr.total_cost = t->trie[0].total_cost;
   for (int l = 0; l < EODM_MAX_N; ++l) tr.off[l] = (l < n) ? t->trie[0].pos[l] : 0;
-  const int grid = grid_for(t, n_tiles, smem);
   cudaError_t e;
-#define CALL(D) launch_fwd<D>(tr, px, mask, NR, T, V, n, n_tiles, n_leaves, part, cnt, grid, smem, st)
-  EODM_DISPATCH_DEPTH(n, CALL)
+#define CALL(D, R) launch_fwd_dr<D, R>(tr, px, mask, NR, T, V, n, tl, n_leaves, acc_smem, part, cnt, smem, st)
+  EODM_DISPATCH(n, tl.R, CALL)
 #undef CALL
   if (e != cudaSuccess) {
     eodm_set_error("eodm_counts_fwd_kernel launch failed: %s", cudaGetErrorString(e));
@@ -509,8 +649,8 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   int work = n_leaves > t->n_order0 ? n_leaves : t->n_order0;
   if (work < 1) work = 1;
   const int fb = 256, fg = (work + fb - 1) / fb;
-  eodm_counts_finish_kernel<<<fg, fb, 0, st>>>(part, cnt, grid, n_leaves, t->trie[0].perm, t->d_order0, t->n_order0, S,
-                                               N);
+  eodm_counts_finish_kernel<<<fg, fb, 0, st>>>(part, cnt, tl.grid, n_leaves, t->trie[0].perm, t->d_order0,
+                                               t->n_order0, S, N);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_counts_finish_kernel launch failed: %s", cudaGetErrorString(e));
@@ -523,23 +663,31 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
                            float* dpx, void* ws, cudaStream_t st) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
-  const int TS = 32 * kR;
-  const long long n_tiles_ll = (NR + TS - 1) / TS;
-  if (n_tiles_ll > 0x7fffffff) {
-    eodm_set_error("B*T too large");
+  Tiling tl;
+  auto fits = [&](int R) { return bwd_smem_bytes(R, V, n) <= (size_t)kMaxSmem; };
+  if (!choose_tiling(t, NR, fits, &tl)) {
+    eodm_set_error("trie path: a [V=%d] x 32-row tile does not fit in %d bytes of shared memory", V, kMaxSmem);
     return EODM_EUNSUPPORTED;
   }
-  const int n_tiles = (int)n_tiles_ll;
-  const size_t smem = bwd_smem_bytes(kR, V, n);
-  if (smem > (size_t)kMaxSmem) {
-    eodm_set_error("trie path needs %zu bytes of shared memory (V=%d) > %d", smem, V, kMaxSmem);
-    return EODM_EUNSUPPORTED;
-  }
+  const size_t smem = bwd_smem_bytes(tl.R, V, n);
   float *part, *g;
   int* cnt;
-  ws_carve(t, ws, &part, &cnt, &g);
-  BwdArgs a;
+  uint2* ng;
+  ws_carve(t, ws, &part, &cnt, &g, &ng);
   cudaError_t e;
+  {
+    const long long work = t->total_nodes_padded > t->total_leaves ? t->total_nodes_padded : t->total_leaves;
+    if (work > 0) {
+      eodm_prepare_g_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+          gS, t->d_nodes_all, t->d_node_z, t->total_nodes_padded, t->d_perm_all, t->total_leaves, ng, g);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        eodm_set_error("eodm_prepare_g_kernel launch failed: %s", cudaGetErrorString(e));
+        return EODM_ECUDA;
+      }
+    }
+  }
+  BwdArgs a;
   for (int j = 0; j < EODM_MAX_N; ++j) {
     TrieArg& tr = a.trie[j];
     if (j >= n) {
@@ -548,23 +696,15 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     }
     const EodmTrie& h = t->trie[j];
     tr.nodes = h.nodes;
+    tr.ng = ng + t->node_offset[j];
     tr.units = h.units;
     tr.g = g + h.leaf_offset;
     tr.n_units = h.n_units;
     tr.total_cost = h.total_cost;
     for (int l = 0; l < EODM_MAX_N; ++l) tr.off[l] = (l < n) ? h.pos[l] - j + (n - 1) : 0;
-    if (h.n_leaves > 0) {
-      eodm_permute_g_kernel<<<(h.n_leaves + 255) / 256, 256, 0, st>>>(gS, h.perm, h.n_leaves, g + h.leaf_offset);
-      e = cudaGetLastError();
-      if (e != cudaSuccess) {
-        eodm_set_error("eodm_permute_g_kernel launch failed: %s", cudaGetErrorString(e));
-        return EODM_ECUDA;
-      }
-    }
   }
-  const int grid = grid_for(t, n_tiles, smem);
-#define CALL(D) launch_bwd<D>(a, px, mask, NR, T, V, n, n_tiles, dpx, grid, smem, st)
-  EODM_DISPATCH_DEPTH(n, CALL)
+#define CALL(D, R) launch_bwd_dr<D, R>(a, px, mask, NR, T, V, n, tl, dpx, smem, st)
+  EODM_DISPATCH(n, tl.R, CALL)
 #undef CALL
   if (e != cudaSuccess) {
     eodm_set_error("eodm_counts_bwd_kernel launch failed: %s", cudaGetErrorString(e));

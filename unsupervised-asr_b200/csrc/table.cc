@@ -200,6 +200,12 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
   t->d_inv_zj = nullptr;
   t->d_order = nullptr;
   t->sm_count = 0;
+  t->d_nodes_all = nullptr;
+  t->d_node_z = nullptr;
+  t->d_perm_all = nullptr;
+  t->total_nodes_padded = 0;
+  std::vector<uint32_t> nodes_all;
+  std::vector<int32_t> node_z_all, perm_all;
   t->ids.assign(ids, ids + (size_t)K * n);
   t->order.resize(K);
   std::vector<int32_t> order0;
@@ -283,10 +289,49 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
     t->htrie[j].nodes = tb.nodes;
     t->htrie[j].units = tb.units;
     t->htrie[j].perm = tb.perm;
+    // node -> z: walk every unit's slice of the pre-order stream, counting leaves from the unit's leaf cursor
+    t->node_offset[j] = (int64_t)nodes_all.size();
+    {
+      std::vector<int32_t> nz(tb.nodes.size(), -1);
+      for (size_t u = 0; u < tb.units.size(); ++u) {
+        if ((tb.units[u].root_flags >> 16) & EODM_UNIT_SELF) continue;
+        uint32_t c0 = tb.units[u].node_cursor, leaf = tb.units[u].leaf_cursor;
+        uint32_t c1 = (uint32_t)tb.nodes.size();
+        for (size_t v = u + 1; v < tb.units.size(); ++v)
+          if (!((tb.units[v].root_flags >> 16) & EODM_UNIT_SELF)) {
+            c1 = tb.units[v].node_cursor;
+            break;
+          }
+        for (uint32_t c = c0; c < c1; ++c)
+          if (EODM_NODE_HASZ(tb.nodes[c])) nz[c] = tb.perm[leaf++];
+      }
+      nodes_all.insert(nodes_all.end(), tb.nodes.begin(), tb.nodes.end());
+      nodes_all.push_back(0);
+      node_z_all.insert(node_z_all.end(), nz.begin(), nz.end());
+      node_z_all.push_back(-1);
+      perm_all.insert(perm_all.end(), tb.perm.begin(), tb.perm.end());
+    }
     if (host_only) continue;
-    if ((rc = upload(t, tb.nodes, &tr.nodes)) != EODM_OK) break;
     if ((rc = upload(t, tb.units, &tr.units)) != EODM_OK) break;
-    if ((rc = upload(t, tb.perm, &tr.perm)) != EODM_OK) break;
+  }
+  t->total_nodes_padded = (int64_t)nodes_all.size();
+  if (rc == EODM_OK && !host_only) {
+    const uint32_t* du = nullptr;
+    const int32_t* di = nullptr;
+    rc = upload(t, nodes_all, &du);
+    t->d_nodes_all = (uint32_t*)du;
+    if (rc == EODM_OK) {
+      rc = upload(t, node_z_all, &di);
+      t->d_node_z = (int32_t*)di;
+    }
+    if (rc == EODM_OK) {
+      rc = upload(t, perm_all, &di);
+      t->d_perm_all = (int32_t*)di;
+    }
+    for (int j = 0; j < n && rc == EODM_OK; ++j) {
+      t->trie[j].nodes = t->d_nodes_all + t->node_offset[j];
+      t->trie[j].perm = t->d_perm_all + t->trie[j].leaf_offset;
+    }
   }
   t->n_order0 = (int)order0.size();
   if (rc == EODM_OK && !host_only) {

@@ -74,6 +74,13 @@ struct eodm_table {
   int32_t* d_inv_zj;          // [nnz] packed z * EODM_MAX_N + j
   uint8_t* d_order;           // [K]
   int sm_count;               // multiprocessors of `device`
+  // all tries' node streams back to back (each followed by one zero word of slack), and for every
+  // node the n-gram index z that ends there (-1: none): the backward pass pairs nodes with dloss/dS[z]
+  uint32_t* d_nodes_all;
+  int32_t* d_node_z;
+  int32_t* d_perm_all;        // all tries' leaf -> z maps back to back (offsets: trie[j].leaf_offset)
+  int64_t node_offset[EODM_MAX_N];
+  int64_t total_nodes_padded;
   std::vector<void*> allocs;  // every device allocation, for destroy
 };
 

@@ -73,6 +73,7 @@ SIGNATURES = {
 # test hook, not part of the public header
 _DEBUG_SIGNATURES = {
     "eodm_table_debug_trie": (_i, [_p, _i, _p, _p, _p, _p, _p]),
+    "eodm_debug_set_tiling": (None, [_i, _i]),
 }
 
 for _name, (_res, _args) in list(SIGNATURES.items()) + list(_DEBUG_SIGNATURES.items()):
