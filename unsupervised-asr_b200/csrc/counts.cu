@@ -135,6 +135,7 @@ struct FwdWalk {
     uint32_t e = ahead;
     ++cursor;
     ahead = __ldg(nodes + cursor);  // every trie's stream is followed by one word of slack
+    if ((cursor & 31u) == 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + cursor + 64));
     return e;
   }
   // sum the parked partials: lane l adds half (l >> 4) of row (l & 15); rows are padded to 33 words so the
@@ -314,6 +315,9 @@ struct BwdWalk {
     uint2 e = ahead;
     ++cursor;
     ahead = __ldg(ng + cursor);
+    // the stream is read once, front to back: pull the next 128-byte line into L1 ahead of the walk
+    // (the prefetch may run a few lines past this trie's slice; it stays inside the workspace)
+    if ((cursor & 15u) == 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(ng + cursor + 32));
     return e;
   }
 };
@@ -594,7 +598,7 @@ extern "C" void eodm_debug_set_tiling(int R, int ts) {
 size_t eodm_counts_workspace_bytes(const eodm_table* t) {
   return up256((size_t)t->sm_count * (size_t)t->trie[0].n_leaves * sizeof(float)) +
          up256((size_t)t->sm_count * 2 * sizeof(int)) + up256((size_t)t->total_leaves * sizeof(float)) +
-         up256((size_t)t->total_nodes_padded * sizeof(uint2)) + 256;
+         up256((size_t)t->total_nodes_padded * sizeof(uint2)) + 1024;
 }
 
 static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, float** g, uint2** ng) {

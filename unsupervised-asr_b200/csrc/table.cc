@@ -314,6 +314,9 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
     if (host_only) continue;
     if ((rc = upload(t, tb.units, &tr.units)) != EODM_OK) break;
   }
+  // slack for the kernels' line prefetch past the last trie
+  nodes_all.insert(nodes_all.end(), 128, 0u);
+  node_z_all.insert(node_z_all.end(), 128, -1);
   t->total_nodes_padded = (int64_t)nodes_all.size();
   if (rc == EODM_OK && !host_only) {
     const uint32_t* du = nullptr;
