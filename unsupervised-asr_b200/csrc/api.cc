@@ -46,11 +46,24 @@ static int check_batch(const eodm_table* t, const void* px, const void* mask, in
 // ---------------------------------------------------------------------------
 // counts, loss, softmax, materialising op
 // ---------------------------------------------------------------------------
+// Which kernels serve the counts: 0 = choose (tensor cores when the table allows), 1 = CUDA-core trie walk,
+// 2 = tcgen05 path.  Test hook, not part of the public header.
+static int g_path = 0;
+extern "C" void eodm_debug_set_path(int path) { g_path = path; }
+
+static bool use_tensor_fwd(const eodm_table* t) {
+  if (g_path == 1) return false;
+  if (g_path == 2) return true;
+  return false;  // until the tensor path is the faster one everywhere it applies
+}
+
+static size_t counts_ws_aligned(const eodm_table* t) { return (eodm_counts_workspace_bytes(t) + 255) & ~(size_t)255; }
+
 extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
   (void)B;
   (void)T;
   if (!t || t->device < 0) return 0;
-  return eodm_counts_workspace_bytes(t);
+  return counts_ws_aligned(t) + eodm_tc_workspace_bytes(t);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -58,6 +71,8 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
+  if (use_tensor_fwd(t))
+    return eodm_tc_fwd_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t), (cudaStream_t)stream);
   return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, ws, (cudaStream_t)stream);
 }
 
@@ -266,7 +281,7 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->py, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->gS, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
-  if (e == cudaSuccess) e = cudaMalloc(&s->ws, eodm_counts_workspace_bytes(t));
+  if (e == cudaSuccess) e = cudaMalloc(&s->ws, eodm_workspace_bytes(t, maxB, maxT));
   if (e == cudaSuccess) e = cudaMemcpy(s->py, py_host, (size_t)t->K * sizeof(float), cudaMemcpyHostToDevice);
   if (prev >= 0) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -294,10 +309,10 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   float* S = s->counts;
   float* N = s->counts + t->K;
   int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
-  if (rc == EODM_OK) rc = eodm_counts_fwd_launch(t, s->px, mask, B, T, S, N, s->ws, st);
+  if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);
   if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, S, t->K, N, st);
   if (rc == EODM_OK) rc = eodm_loss_launch(S, N, s->py, t->K, 1e-15f, loss, dlogits ? s->gS : nullptr, st);
-  if (rc == EODM_OK && dlogits) rc = eodm_counts_bwd_launch(t, s->px, mask, B, T, s->gS, s->dpx, s->ws, st);
+  if (rc == EODM_OK && dlogits) rc = eodm_counts_bwd(t, s->px, mask, B, T, s->gS, s->dpx, s->ws, st);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(s->px, s->dpx, rows, t->V, dlogits, st);
   return rc;
 }

@@ -15,6 +15,12 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
                            float* dpx, void* ws, cudaStream_t st);
 
+// tensor.cu -- tcgen05 path for full-order tables
+bool eodm_tc_supported(const eodm_table* t);
+size_t eodm_tc_workspace_bytes(const eodm_table* t);
+int eodm_tc_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
+                       void* ws, cudaStream_t st);
+
 // ops.cu -- loss, softmax, materialising op
 int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
                      cudaStream_t st);

@@ -58,6 +58,16 @@ struct EodmTrieHost {  // host mirror (tests, eodm_table_debug_trie)
   std::vector<int32_t> perm;
 };
 
+// Tensor-core path (tensor.cu): for window position j, the distinct tuples of the tokens at the OTHER
+// positions (ascending position order) are the rows of a dense [rows x V] matrix; n-gram z sits at
+// (zrow[z], ids[z][j]).  Built only when every n-gram has order == n >= 2.
+struct EodmRows {
+  int n_rows;
+  const int32_t* d_tok;   // [n_rows][n-1]
+  const int32_t* d_zrow;  // [K]
+  const int32_t* d_zcol;  // [K]
+};
+
 struct eodm_table {
   int n, V, K, device;        // device == -1: host-only table (no uploads; compute calls reject it)
   EodmTrieHost htrie[EODM_MAX_N];
@@ -79,6 +89,8 @@ struct eodm_table {
   uint32_t* d_nodes_all;
   int32_t* d_node_z;
   int32_t* d_perm_all;        // all tries' leaf -> z maps back to back (offsets: trie[j].leaf_offset)
+  bool full_order;            // every n-gram has order == n
+  EodmRows rows[EODM_MAX_N];
   int64_t node_offset[EODM_MAX_N];
   int64_t total_nodes_padded;
   std::vector<void*> allocs;  // every device allocation, for destroy

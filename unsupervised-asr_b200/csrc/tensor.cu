@@ -1,0 +1,456 @@
+// Expected n-gram counts on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// For a table whose n-grams all have order n, split every n-gram into its prefix p (the first n-1 phones)
+// and its last phone c.  Then
+//     S[p, c] = sum_w  Q[p, w] * Pm[c, w],   Q[p, w] = prod_{j<n-1} (px[w+j, p_j] + eps),
+//                                            Pm[c, w] = mask[w] * (px[w+n-1, c] + eps)
+// is a [rows x W] . [W x V] contraction over the windows w -- a GEMM whose K dimension is the batch.
+// Only K of its rows*V outputs are n-grams of the table (10 % for random top-10k trigrams over 47
+// phones), but the sparse walk of counts.cu needs one shared-memory operand per (n-gram, window) and
+// is bound by shared-memory bandwidth, whereas here the operand reuse happens inside the tensor core:
+// the dense product is cheaper than the sparse one.
+//
+// Mapping.  The M dimension (128 TMEM lanes) is the prefix row, N is the last phone (V padded to 16),
+// K is the window index, 8 windows (one tf32 MMA K step) per chunk.  A CTA owns up to 6 M tiles whose
+// fp32 accumulators D[128 x Npad] stay resident in TMEM for the CTA's whole slice of the batch; CTAs
+// are arranged as (M-tile group) x (batch slice).  The A operand never touches shared memory: the
+// producer threads (thread = TMEM lane = prefix row) form Q for 8 windows in registers from a staged
+// px tile and write it to TMEM with tcgen05.st; the B operand (8 windows x Npad phones) is written to
+// shared memory in the canonical K-major no-swizzle layout.  fp32 accuracy comes from the 3xTF32
+// split: x = hi + lo with hi = x rounded to 10 mantissa bits toward zero, and
+//     D += A_hi B_hi + A_lo B_hi + A_hi B_lo            (the dropped lo*lo term is 2^-22 relative).
+// MMAs are issued by one thread and complete asynchronously (tcgen05.commit -> mbarrier) while all
+// warps produce the next chunk into the other TMEM/shared stage.  At the end every CTA writes its
+// accumulators to a per-slice partial, and a second kernel gathers the K table entries and adds the
+// slices in a fixed order: deterministic, no float atomics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eodm_b200.h"
+#include "kernels.h"
+#include "table.h"
+
+namespace {
+
+constexpr int kProd = 512;             // producer threads: 4 warpgroups, one M tile each
+constexpr int kTThreads = kProd + 32;  // + the MMA-issuing warp
+constexpr int kKC = 8;                 // windows per chunk = K of one tf32 MMA
+constexpr int kSuper = 128;            // windows per staged px tile
+constexpr int kDR = kSuper / kKC;      // chunks per accumulation round (see "rounds" below)
+constexpr int kMaxMT = 4;              // M tiles per CTA
+constexpr uint32_t kTmemCols = 512;
+constexpr float kEps = 1e-15f;
+
+struct TcFwdArgs {
+  const float* px;
+  const uint8_t* mask;
+  const int32_t* tok;  // [n_rows][n-1]
+  float* partS;        // [n_slices][n_mtiles * 128][Npad]
+  long long NR, rows_per_slice;
+  int T, V, n, n_rows, n_mtiles, MT, G_m, n_slices, Npad;
+};
+
+struct TcBars {
+  uint64_t a_full[kMaxMT][2], a_free[kMaxMT][2], b_full[2], b_free[2], d_full[2], d_empty[2];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two 16-byte K halves,
+// SBO = distance between 8-row groups (both in bytes, encoded >> 4); descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]; tf32 inputs, fp32 accumulation, M = 128, cta_group 1
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const uint32_t h = __float_as_uint(x) & 0xffffe000u;
+  hi = h;
+  lo = __float_as_uint(x - __uint_as_float(h));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory"); }
+
+// Rounds.  The tensor core adds every MMA's partial sum into the fp32 accumulator with truncation, so a long
+// accumulation chain drifts low (measured: -3.7e-8 relative per MMA; -3e-5 over a slice of 2000 windows).
+// The accumulators therefore live in TMEM for one round of kDR chunks only (48 MMAs per element), then are
+// added -- round-to-nearest -- to fp32 sums held in the producer threads' registers; two TMEM banks
+// alternate so the drain of one round overlaps the MMAs of the next.
+template <int NP, int NPAD>  // prefix length n-1; V padded to a multiple of 16
+__global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int V = a.V, n = a.n, VS = a.V + 1;            // px tile rows carry one extra, zero, column
+  constexpr int b_floats = NPAD * kKC;                  // one B operand (hi or lo) of one stage
+  float* Bs = reinterpret_cast<float*>(smem_raw);       // [2 stages][hi, lo][NPAD * 8]
+  float* wm = Bs + 4 * b_floats;                        // [kSuper]
+  float* Pt = wm + kSuper;                              // [kSuper + n - 1][V + 1]
+  __shared__ __align__(8) TcBars bars;
+  __shared__ uint32_t tmem_slot;
+
+  const int mg = blockIdx.x % a.G_m, slice = blockIdx.x / a.G_m;
+  if (slice >= a.n_slices) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, quarter = warp & 3, l128 = tid & 127;
+  const int MT = min(a.MT, a.n_mtiles - mg * a.MT);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int g = 0; g < kMaxMT; ++g)
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars.a_full[g][s], 4);  // the four warps of the producing warpgroup
+        mbar_init(&bars.a_free[g][s], 1);  // tcgen05.commit
+      }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.b_full[s], kProd / 32);
+      mbar_init(&bars.b_free[s], 1);
+      mbar_init(&bars.d_full[s], 1);
+      mbar_init(&bars.d_empty[s], 4 * MT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t colA0 = (uint32_t)(2 * a.MT * NPAD);  // A stages follow the two accumulator banks
+  const long long w_begin = (long long)slice * a.rows_per_slice;
+  const long long w_end = (w_begin + a.rows_per_slice < a.NR) ? w_begin + a.rows_per_slice : a.NR;
+  const int total_chunks = w_end > w_begin ? (int)((w_end - w_begin + kKC - 1) / kKC) : 0;
+
+  if (warp == kProd / 32) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+      for (int i = 0; i < total_chunks; ++i) {
+        const int s = i & 1, use = i >> 1, r = i / kDR, bank = r & 1;
+        const bool first = (i % kDR) == 0;
+        if (first && r >= 2) mbar_wait(&bars.d_empty[bank], (uint32_t)(((r >> 1) - 1) & 1));
+        mbar_wait(&bars.b_full[s], (uint32_t)(use & 1));
+        const uint32_t bhi_addr = smem_u32(Bs + (2 * s) * b_floats);
+        const uint64_t dhi = smem_desc_kmajor(bhi_addr, (uint32_t)NPAD * 16u, 128u);
+        const uint64_t dlo = smem_desc_kmajor(bhi_addr + (uint32_t)b_floats * 4u, (uint32_t)NPAD * 16u, 128u);
+        for (int g = 0; g < MT; ++g) {
+          mbar_wait(&bars.a_full[g][s], (uint32_t)(use & 1));
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)((bank * a.MT + g) * NPAD);
+          const uint32_t ahi = tmem + colA0 + (uint32_t)((g * 2 + s) * 16), alo = ahi + 8;
+          mma_tf32_ts(d, ahi, dhi, idesc, first ? 0u : 1u);
+          mma_tf32_ts(d, alo, dhi, idesc, 1u);
+          mma_tf32_ts(d, ahi, dlo, idesc, 1u);
+          mma_commit(&bars.a_free[g][s]);
+        }
+        mma_commit(&bars.b_free[s]);
+        if ((i % kDR) == kDR - 1 || i == total_chunks - 1) mma_commit(&bars.d_full[bank]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ producers
+    const bool active = wg < MT;  // warpgroup wg owns M tile wg of this CTA's group
+    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    const int row = (mg * a.MT + wg) * 128 + l128;
+    int tok[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) tok[j] = (active && row < a.n_rows) ? __ldg(a.tok + (size_t)row * NP + j) : V;
+    float acc[NPAD];
+#pragma unroll
+    for (int k = 0; k < NPAD; ++k) acc[k] = 0.f;
+
+    auto drain = [&](int r) {  // add round r's TMEM accumulators into the register sums
+      const int bank = r & 1;
+      mbar_wait(&bars.d_full[bank], (uint32_t)((r >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cg = 0; cg < NPAD; cg += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_field + (uint32_t)((bank * a.MT + wg) * NPAD + cg), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[cg + k] += __uint_as_float(v[k]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.d_empty[bank]);
+    };
+
+    int i = 0;
+    for (long long st0 = w_begin; st0 < w_end; st0 += kSuper) {
+      bar_sync_producers();  // every reader of the previous px tile is done
+      {
+        const int nrows = kSuper + n - 1;
+        for (int idx = tid; idx < nrows * VS; idx += kProd) {
+          const int rr = idx / VS, cc = idx - rr * VS;
+          const long long gr = st0 + rr;
+          Pt[idx] = (cc < V && gr < a.NR) ? __ldg(a.px + gr * V + cc) + kEps : 0.f;
+        }
+        if (tid < kSuper) {
+          const long long wrow = st0 + tid;
+          float ok = 0.f;
+          if (wrow < w_end) {
+            const int t = (int)(wrow % a.T);
+            ok = (t <= a.T - n && __ldg(a.mask + wrow) != 0) ? 1.f : 0.f;
+          }
+          wm[tid] = ok;
+        }
+      }
+      bar_sync_producers();
+      const long long left = w_end - st0;
+      const int nchunks = (int)(((left < kSuper ? left : kSuper) + kKC - 1) / kKC);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c, ++i) {
+        const int s = i & 1, use = i >> 1;
+        const int w0 = c * kKC;
+        if (active) {
+          if (use > 0) {
+            mbar_wait(&bars.a_free[wg][s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage are done
+            tc_fence_after();
+          }
+          uint32_t r[16];
+          const float* cb = Pt + w0 * VS;
+#pragma unroll
+          for (int w = 0; w < kKC; ++w) {
+            float q = cb[w * VS + tok[0]];  // dead rows read the zero column
+#pragma unroll
+            for (int j = 1; j < NP; ++j) q *= cb[(w + j) * VS + tok[j]];
+            split_tf32(q, r[w], r[8 + w]);
+          }
+          tmem_st16(tmem + lane_field + colA0 + (uint32_t)((wg * 2 + s) * 16), r);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a_full[wg][s]);
+        }
+        // this thread's share of the B operand: 8 windows x NPAD phones, masked, hi and lo
+        if (use > 0) mbar_wait(&bars.b_free[s], (uint32_t)((use - 1) & 1));
+        if (tid < b_floats) {
+          const int cc = tid >> 3, w = tid & 7;
+          float v = 0.f;
+          if (cc < V) v = Pt[(w0 + w + n - 1) * VS + cc] * wm[w0 + w];
+          uint32_t hi, lo;
+          split_tf32(v, hi, lo);
+          const int off = (w >> 2) * (NPAD * 4) + (cc >> 3) * 32 + (cc & 7) * 4 + (w & 3);
+          float* Bhi = Bs + (2 * s) * b_floats;
+          Bhi[off] = __uint_as_float(hi);
+          Bhi[b_floats + off] = __uint_as_float(lo);
+          fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.b_full[s]);
+        // the previous round's accumulators, once this round's first chunk is on its way
+        if (active && i > 0 && (i % kDR) == 0) drain(i / kDR - 1);
+      }
+    }
+    if (active) {
+      if (i > 0) drain((i - 1) / kDR);
+      float* out = a.partS + ((size_t)slice * a.n_mtiles * 128 + row) * NPAD;
+#pragma unroll
+      for (int k = 0; k < NPAD; k += 4)
+        *reinterpret_cast<float4*>(out + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// S[z] = sum over slices (fixed order) of partS[slice][zrow[z]][zcol[z]];  N = number of valid frames
+__global__ void __launch_bounds__(256) eodm_tc_finish_kernel(const float* __restrict__ partS, int n_slices,
+                                                             long long slice_stride, int Npad,
+                                                             const int32_t* __restrict__ zrow,
+                                                             const int32_t* __restrict__ zcol, int K,
+                                                             const uint8_t* __restrict__ mask, long long NR,
+                                                             float* __restrict__ S, float* __restrict__ N) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z < K) {
+    const float* p = partS + (size_t)zrow[z] * Npad + zcol[z];
+    float s = 0.f;
+    for (int sl = 0; sl < n_slices; ++sl) s += p[(size_t)sl * slice_stride];
+    S[z] = s;
+  }
+  if (blockIdx.x == gridDim.x - 1 && N) {  // the last block also counts the frames (integer arithmetic: exact)
+    __shared__ int red[256];
+    int c = 0;
+    for (long long i = threadIdx.x; i < NR; i += blockDim.x) c += mask[i] != 0;
+    red[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) N[0] = (float)red[0];
+  }
+}
+
+struct TcPlan {
+  int Npad, n_mtiles, MT, G_m, n_slices;
+  long long rows_per_slice;
+  size_t smem, part_bytes;
+};
+
+bool tc_plan(const eodm_table* t, long long NR, TcPlan* p) {
+  if (!t->full_order || t->n < 2 || t->n > 5) return false;
+  const int j = t->n - 1;
+  const int Npad = (t->V + 15) & ~15;
+  if (Npad > 64) return false;  // one register accumulator per padded phone and producer thread
+  int mt_max = 512 / (2 * Npad + 32);
+  if (mt_max > kMaxMT) mt_max = kMaxMT;
+  const int n_mtiles = (t->rows[j].n_rows + 127) / 128;
+  const int G_m = (n_mtiles + mt_max - 1) / mt_max;
+  if (G_m > t->sm_count) return false;
+  p->Npad = Npad;
+  p->n_mtiles = n_mtiles;
+  p->G_m = G_m;
+  p->MT = (n_mtiles + G_m - 1) / G_m;
+  int n_slices = t->sm_count / G_m;
+  long long rps = (NR + n_slices - 1) / n_slices;
+  rps = (rps + kKC - 1) / kKC * kKC;
+  if (rps < kKC) rps = kKC;
+  n_slices = (int)((NR + rps - 1) / rps);
+  p->n_slices = n_slices;
+  p->rows_per_slice = rps;
+  p->smem = sizeof(float) * ((size_t)4 * Npad * kKC + kSuper + (size_t)(kSuper + t->n - 1) * (t->V + 1)) + 128;
+  p->part_bytes = sizeof(float) * (size_t)n_slices * n_mtiles * 128 * Npad;
+  return p->smem <= 200 * 1024;
+}
+
+}  // namespace
+
+// Can the tensor-core path serve this table at all (shape-independent part)?
+bool eodm_tc_supported(const eodm_table* t) {
+  TcPlan p;
+  return tc_plan(t, 1 << 20, &p);
+}
+
+// Upper bound of the partial-accumulator scratch for any batch (n_slices <= sm_count / G_m).
+size_t eodm_tc_workspace_bytes(const eodm_table* t) {
+  TcPlan p;
+  if (!tc_plan(t, 1LL << 40, &p)) return 0;
+  const size_t slices = (size_t)(t->sm_count / p.G_m);
+  return sizeof(float) * slices * p.n_mtiles * 128 * p.Npad + 256;
+}
+
+int eodm_tc_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
+                       void* ws, cudaStream_t st) {
+  const long long NR = (long long)B * T;
+  TcPlan p;
+  if (!tc_plan(t, NR, &p)) {
+    eodm_set_error("tensor-core path does not cover this table (needs every order == n in [2,5], V <= 256)");
+    return EODM_EUNSUPPORTED;
+  }
+  const int j = t->n - 1;
+  TcFwdArgs a;
+  a.px = px;
+  a.mask = mask;
+  a.tok = t->rows[j].d_tok;
+  a.partS = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  a.NR = NR;
+  a.rows_per_slice = p.rows_per_slice;
+  a.T = T;
+  a.V = t->V;
+  a.n = t->n;
+  a.n_rows = t->rows[j].n_rows;
+  a.n_mtiles = p.n_mtiles;
+  a.MT = p.MT;
+  a.G_m = p.G_m;
+  a.n_slices = p.n_slices;
+  a.Npad = p.Npad;
+  const int grid = p.n_slices * p.G_m;
+  cudaError_t e = cudaSuccess;
+#define LAUNCH(NP, NPAD)                                                                                      \
+  do {                                                                                                        \
+    e = cudaFuncSetAttribute(eodm_tc_fwd_kernel<NP, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             (int)p.smem);                                                                    \
+    if (e == cudaSuccess) {                                                                                   \
+      eodm_tc_fwd_kernel<NP, NPAD><<<grid, kTThreads, p.smem, st>>>(a);                                       \
+      e = cudaGetLastError();                                                                                 \
+    }                                                                                                         \
+  } while (0)
+#define LAUNCH_NP(NPAD)                \
+  switch (t->n - 1) {                  \
+    case 1: LAUNCH(1, NPAD); break;    \
+    case 2: LAUNCH(2, NPAD); break;    \
+    case 3: LAUNCH(3, NPAD); break;    \
+    default: LAUNCH(4, NPAD); break;   \
+  }
+  switch (p.Npad) {
+    case 16: LAUNCH_NP(16) break;
+    case 32: LAUNCH_NP(32) break;
+    case 48: LAUNCH_NP(48) break;
+    default: LAUNCH_NP(64) break;
+  }
+#undef LAUNCH_NP
+#undef LAUNCH
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_tc_fwd_kernel launch failed: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  eodm_tc_finish_kernel<<<(t->K + 255) / 256, 256, 0, st>>>(a.partS, p.n_slices, (long long)p.n_mtiles * 128 * p.Npad,
+                                                            p.Npad, t->rows[j].d_zrow, t->rows[j].d_zcol, t->K, mask,
+                                                            NR, S, N);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_tc_finish_kernel launch failed: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}

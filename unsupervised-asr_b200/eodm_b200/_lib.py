@@ -74,6 +74,7 @@ SIGNATURES = {
 _DEBUG_SIGNATURES = {
     "eodm_table_debug_trie": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "eodm_debug_set_tiling": (None, [_i, _i]),
+    "eodm_debug_set_path": (None, [_i]),
 }
 
 for _name, (_res, _args) in list(SIGNATURES.items()) + list(_DEBUG_SIGNATURES.items()):
