@@ -139,6 +139,26 @@ def test_every_tile_variant(eodm, case):
         lib.eodm_debug_set_tiling(0, 0)
 
 
+@pytest.mark.parametrize("seed,V,n,K,B,T", [(1, 16, 2, 100, 3, 40), (2, 48, 3, 3000, 5, 150), (3, 40, 5, 1000, 6, 70),
+                                             (4, 48, 3, 10000, 40, 300), (5, 64, 4, 2500, 4, 90)])
+def test_tensor_core_counts_vs_oracle(eodm, seed, V, n, K, B, T):
+    """The tcgen05 forward path (3xTF32, accumulators drained every 16 MMA steps), pinned through the debug hook."""
+    from eodm_b200._lib import lib
+    ids, py = eodm.synth.table(V, n, K, seed=seed)
+    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=n)
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    S_ref, N_ref = O.counts_fwd(px.cpu().numpy().astype(np.float64), mask, ids, n)
+    try:
+        lib.eodm_debug_set_path(2)
+        counts = eodm.counts_fwd(table, px, torch.tensor(mask, device=dev)).cpu().numpy()
+    finally:
+        lib.eodm_debug_set_path(0)
+    assert counts[K] == N_ref
+    assert (np.abs(counts[:K] - S_ref) / S_ref).max() <= TOL
+
+
 @pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", [CASES[1], CASES[5], CASES[7]])
 def test_eodm_loss_end_to_end_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
     ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
@@ -190,12 +210,16 @@ def test_materialising_op_and_vjp(eodm):
 
 def test_softmax_kernels(eodm):
     dev = _dev()
-    x = torch.randn(37, 5, 48, device=dev) * 5
-    px = eodm.softmax_fwd(x)
-    assert torch.allclose(px, torch.softmax(x, -1), rtol=1e-6, atol=1e-9)
-    d = torch.randn_like(px)
-    ref = px * (d - (px * d).sum(-1, keepdim=True))
-    assert torch.allclose(eodm.softmax_bwd(px, d), ref, rtol=1e-5, atol=1e-7)
+    torch.manual_seed(0)
+    for V in (48, 40, 4, 128, 33, 200, 72):      # vectorised groups of 1..32 lanes, and the generic path
+        x = torch.randn(37, 5, V, device=dev) * 5
+        px = eodm.softmax_fwd(x)
+        ref = torch.softmax(x.double(), -1)
+        assert float(((px.double() - ref).abs() / ref).max()) <= 2e-6, V
+        d = torch.randn_like(px)
+        ref = px.double() * (d.double() - (px.double() * d.double()).sum(-1, keepdim=True))
+        got = eodm.softmax_bwd(px, d).double()
+        assert float((got - ref).abs().max() / ref.abs().max()) <= 1e-6, V
 
 
 def test_edge_cases_and_errors(eodm):

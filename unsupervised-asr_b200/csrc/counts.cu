@@ -38,7 +38,10 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef EODM_WALK_THREADS
+#define EODM_WALK_THREADS 512
+#endif
+constexpr int kThreads = EODM_WALK_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr float kEps = 1e-15f;  // models/EODM.py:63
 constexpr int kStageLeaves = 16;
@@ -48,8 +51,9 @@ struct TrieArg {
   const uint32_t* nodes;  // forward: node words
   const uint2* ng;        // backward: (node word, dloss/dS of the n-gram ending there or 0)
   const EodmUnit* units;
+  const EodmRoot* roots;
   const float* g;         // backward: dloss/dS in this trie's leaf order (for n-grams ending at the root)
-  int n_units;
+  int n_units, n_roots;
   uint32_t total_cost;
   int off[EODM_MAX_N];  // level -> column offset inside the staged tile
 };
@@ -76,6 +80,17 @@ __device__ __forceinline__ void warp_unit_range(const TrieArg& tr, int warp, int
   uint32_t t1 = (uint32_t)(((uint64_t)tr.total_cost * (warp + 1)) / kWarps);
   lo = unit_lower_bound(tr.units, tr.n_units, t0);
   hi = (warp + 1 == kWarps) ? tr.n_units : unit_lower_bound(tr.units, tr.n_units, t1);
+}
+
+// the root whose units contain unit u (roots are sorted by first_unit; root 0 starts at unit 0)
+__device__ __forceinline__ int root_of_unit(const TrieArg& tr, int u) {
+  int lo = 0, hi = tr.n_roots;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if ((int)__ldg(&tr.roots[mid].first_unit) <= u) lo = mid;
+    else hi = mid;
+  }
+  return lo;
 }
 
 // Stage rows [row0, row0 + nrows) of px, plus eps, transposed into Ps[v][ld]; columns nrows .. ncols-1 and
@@ -235,28 +250,37 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
     float wmv[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) wmv[r] = wm[lane + 32 * r];
-    int prev_root = -1;
     float q0[R];
     w.pend = 0;
+    bool first_seg = true;
+    // roots whose units intersect this warp's share; within a root the n-grams ending at the root come first,
+    // then its depth-2 subtrees, contiguous in the node stream
 #pragma unroll 1
-    for (int u = u_lo; u < u_hi; ++u) {
-      const uint4 un = __ldg(reinterpret_cast<const uint4*>(tr.units) + u);
-      const int root = un.z & 0xffff;
-      if (u == u_lo) w.leaf0 = un.y;
-      if (root != prev_root) {
-        const float* row = Pl + root * ld + tr.off[0];
-#pragma unroll
-        for (int r = 0; r < R; ++r) q0[r] = row[32 * r] * wmv[r];
-        prev_root = root;
+    for (int ri = (u_lo < u_hi) ? root_of_unit(tr, u_lo) : tr.n_roots; ri < tr.n_roots; ++ri) {
+      const uint4 rt = __ldg(reinterpret_cast<const uint4*>(tr.roots) + ri);
+      if ((int)rt.y >= u_hi) break;
+      const int lo = max(u_lo, (int)rt.y), hi = min(u_hi, (int)(rt.y + rt.w));
+      const int n_self = max(0, min(hi, (int)(rt.y + rt.z)) - lo);
+      const int n_sub = (hi - lo) - n_self;
+      const uint4 un = __ldg(reinterpret_cast<const uint4*>(tr.units) + lo + (n_sub ? n_self : 0));
+      if (first_seg) {
+        w.leaf0 = n_self ? __ldg(&tr.units[lo].leaf_cursor) : un.y;
+        first_seg = false;
       }
-      if ((un.z >> 16) & EODM_UNIT_SELF) {
+      const float* row = Pl + rt.x * ld + tr.off[0];
+#pragma unroll
+      for (int r = 0; r < R; ++r) q0[r] = row[32 * r] * wmv[r];
+      if (n_self) {
         float s = q0[0];
 #pragma unroll
         for (int r = 1; r < R; ++r) s += q0[r];
-        w.emit(s);
-      } else if constexpr (DEPTH > 1) {
-        w.seek(un.x);
-        fwd_visit<1, DEPTH, R>(w, tr, Pl, ld, q0, 1);
+        for (int k = 0; k < n_self; ++k) w.emit(s);
+      }
+      if constexpr (DEPTH > 1) {
+        if (n_sub) {
+          w.seek(un.x);
+          fwd_visit<1, DEPTH, R>(w, tr, Pl, ld, q0, n_sub);
+        }
       }
     }
     if (w.pend) w.flush();
@@ -269,26 +293,29 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
   if (threadIdx.x < 2) part_cnt[blockIdx.x * 2 + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
-// S[perm[leaf]] = sum over CTAs (fixed order) of part[cta][leaf]; order-0 n-grams get the
-// number of valid windows; N = number of valid frames.
+// S[perm[leaf]] = sum over CTAs (fixed order) of part[cta][leaf]; order-0 n-grams get the number of valid
+// windows; N = number of valid frames.  Block = 32 leaves x 8 CTA groups: thread (x, y) adds CTAs y, y+8, ...
+// (coalesced 128-byte rows), then the 8 group sums are added in order.
 __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __restrict__ part,
                                                                  const int* __restrict__ part_cnt, int n_cta,
                                                                  int n_leaves, const int32_t* __restrict__ perm,
                                                                  const int32_t* __restrict__ order0, int n_order0,
                                                                  float* __restrict__ S, float* __restrict__ N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_leaves) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains; the order is fixed
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-      s0 += part[(size_t)c * n_leaves + i];
-      s1 += part[(size_t)(c + 1) * n_leaves + i];
-      s2 += part[(size_t)(c + 2) * n_leaves + i];
-      s3 += part[(size_t)(c + 3) * n_leaves + i];
-    }
-    for (; c < n_cta; ++c) s0 += part[(size_t)c * n_leaves + i];
-    S[perm[i]] = (s0 + s1) + (s2 + s3);
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int leaf = blockIdx.x * 32 + x;
+  float s = 0.f;
+  if (leaf < n_leaves)
+    for (int c = y; c < n_cta; c += 8) s += part[(size_t)c * n_leaves + leaf];
+  red[y][x] = s;
+  __syncthreads();
+  if (y == 0 && leaf < n_leaves) {
+    float t = red[0][x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][x];
+    S[perm[leaf]] = t;
   }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_order0 || i == 0) {
     long long cn = 0, cw = 0;
     for (int c = 0; c < n_cta; ++c) {
@@ -390,7 +417,6 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
 #pragma unroll
         for (int r = 0; r < R; ++r) wmv[r] = wm[lane + 32 * r - j + (n - 1)];
         int cur_root = -1, n_side = 0;
-        bool head_complete = false;
         float acc[R];
         auto flush = [&](bool complete) {
           if (complete) {
@@ -406,30 +432,30 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
           }
         };
 #pragma unroll 1
-        for (int u = u_lo; u < u_hi; ++u) {
-          const uint4 un = __ldg(reinterpret_cast<const uint4*>(tr.units) + u);
-          const int root = un.z & 0xffff;
-          const uint32_t flags = un.z >> 16;
-          if (root != cur_root || (flags & EODM_UNIT_FIRST)) {
-            if (cur_root >= 0) flush(head_complete);
-            cur_root = root;
-            head_complete = (flags & EODM_UNIT_FIRST) != 0;
+        for (int ri = (u_lo < u_hi) ? root_of_unit(tr, u_lo) : tr.n_roots; ri < tr.n_roots; ++ri) {
+          const uint4 rt = __ldg(reinterpret_cast<const uint4*>(tr.roots) + ri);
+          if ((int)rt.y >= u_hi) break;
+          const int lo = max(u_lo, (int)rt.y), hi = min(u_hi, (int)(rt.y + rt.w));
+          const int n_self = max(0, min(hi, (int)(rt.y + rt.z)) - lo);
+          const int n_sub = (hi - lo) - n_self;
+          cur_root = (int)rt.x;
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0.f;
-          }
-          if (flags & EODM_UNIT_SELF) {
-            const float g = __ldg(tr.g + un.y);
+          for (int r = 0; r < R; ++r) acc[r] = 0.f;
+          if (n_self) {  // n-grams that are just (root): d/dP[root] = g * mask
+            const uint32_t g0 = __ldg(&tr.units[lo].leaf_cursor);
+            float gs = 0.f;
+            for (int k = 0; k < n_self; ++k) gs += __ldg(tr.g + g0 + k);
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] += g;
-          } else if constexpr (DEPTH > 1) {
-            w.seek(un.x);
-            bwd_visit<1, DEPTH, R>(w, tr, Pl, ld, acc, 1);
+            for (int r = 0; r < R; ++r) acc[r] = gs;
           }
-        }
-        if (cur_root >= 0) {
-          bool tail_complete = true;
-          if (u_hi < tr.n_units) tail_complete = ((__ldg(&tr.units[u_hi].root_flags) >> 16) & EODM_UNIT_FIRST) != 0;
-          flush(head_complete && tail_complete);
+          if constexpr (DEPTH > 1) {
+            if (n_sub) {
+              w.seek(__ldg(&tr.units[lo + n_self].node_cursor));
+              bwd_visit<1, DEPTH, R>(w, tr, Pl, ld, acc, n_sub);
+            }
+          }
+          // a root cut by a warp boundary goes through the side buffer and is added in warp order
+          flush(lo == (int)rt.y && hi == (int)(rt.y + rt.w));
         }
         __syncthreads();
         // roots shared between neighbouring warps: add their partial sums in warp order
@@ -483,7 +509,7 @@ size_t bwd_smem_bytes(int R, int V, int n) {
 }
 
 // windows-per-lane variants compiled for a given trie depth (register budget: R floats per level)
-constexpr int kRs[] = {12, 8, 4, 1};
+constexpr int kRs[] = {12, 11, 8, 4, 1};
 __host__ inline bool r_allowed(int depth, int R) { return R <= 8 || depth <= 5; }
 
 // Tile height: the smallest number of equal row slices per SM such that a slice fits the lanes.
@@ -564,6 +590,7 @@ cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask
 #define EODM_DISPATCH_R(D, R, CALL)                   \
   switch (R) {                                        \
     case 12: e = CALL(D, 12); break;                  \
+    case 11: e = CALL(D, 11); break;                  \
     case 8: e = CALL(D, 8); break;                    \
     case 4: e = CALL(D, 4); break;                    \
     default: e = CALL(D, 1); break;                   \
@@ -638,6 +665,8 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   tr.nodes = t->trie[0].nodes;
   tr.ng = nullptr;
   tr.units = t->trie[0].units;
+  tr.roots = t->trie[0].roots;
+  tr.n_roots = t->trie[0].n_roots;
   tr.g = nullptr;
   tr.n_units = t->trie[0].n_units;
   tr.total_cost = t->trie[0].total_cost;
@@ -650,9 +679,10 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     eodm_set_error("eodm_counts_fwd_kernel launch failed: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
   }
-  int work = n_leaves > t->n_order0 ? n_leaves : t->n_order0;
-  if (work < 1) work = 1;
-  const int fb = 256, fg = (work + fb - 1) / fb;
+  int fg = (n_leaves + 31) / 32;
+  if (fg < (t->n_order0 + 255) / 256) fg = (t->n_order0 + 255) / 256;
+  if (fg < 1) fg = 1;
+  const int fb = 256;
   eodm_counts_finish_kernel<<<fg, fb, 0, st>>>(part, cnt, tl.grid, n_leaves, t->trie[0].perm, t->d_order0,
                                                t->n_order0, S, N);
   e = cudaGetLastError();
@@ -702,6 +732,8 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     tr.nodes = h.nodes;
     tr.ng = ng + t->node_offset[j];
     tr.units = h.units;
+    tr.roots = h.roots;
+    tr.n_roots = h.n_roots;
     tr.g = g + h.leaf_offset;
     tr.n_units = h.n_units;
     tr.total_cost = h.total_cost;

@@ -48,7 +48,49 @@ __global__ void __launch_bounds__(1024) eodm_loss_kernel(const float* __restrict
   }
 }
 
-// one warp per row
+// Softmax over rows of V floats.  A row is held in registers by a group of G lanes (G = 1..32, a power of two,
+// 4 floats per lane), so a warp covers 32/G rows with one vectorised read and one vectorised write per element:
+// HBM-bound (8 B per element forward, 12 B backward).  Rows wider than 128 floats take the generic warp-per-row path.
+template <int G>
+__global__ void __launch_bounds__(256) eodm_softmax_fwd_vec_kernel(const float* __restrict__ x, int64_t rows, int V,
+                                                                   float* __restrict__ y) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int gl = threadIdx.x % G;
+  const bool live = row < rows && gl * 4 < V;
+  float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  if (live) v = __ldg(reinterpret_cast<const float4*>(x + row * V) + gl);
+  float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) e = make_float4(expf(v.x - m), expf(v.y - m), expf(v.z - m), expf(v.w - m));
+  float s = (e.x + e.y) + (e.z + e.w);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (live) reinterpret_cast<float4*>(y + row * V)[gl] = make_float4(e.x / s, e.y / s, e.z / s, e.w / s);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) eodm_softmax_bwd_vec_kernel(const float* __restrict__ px,
+                                                                   const float* __restrict__ dpx, int64_t rows, int V,
+                                                                   float* __restrict__ dx) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int gl = threadIdx.x % G;
+  const bool live = row < rows && gl * 4 < V;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), d = p;
+  if (live) {
+    p = __ldg(reinterpret_cast<const float4*>(px + row * V) + gl);
+    d = __ldg(reinterpret_cast<const float4*>(dpx + row * V) + gl);
+  }
+  float s = fmaf(p.x, d.x, fmaf(p.y, d.y, fmaf(p.z, d.z, p.w * d.w)));
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (live)
+    reinterpret_cast<float4*>(dx + row * V)[gl] =
+        make_float4(p.x * (d.x - s), p.y * (d.y - s), p.z * (d.z - s), p.w * (d.w - s));
+}
+
+// generic: one warp per row
 __global__ void __launch_bounds__(256) eodm_softmax_fwd_kernel(const float* __restrict__ x, int64_t rows, int V,
                                                                float* __restrict__ y) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -148,8 +190,35 @@ int eodm_loss_launch(const float* S, const float* N, const float* py, int K, flo
   return EODM_OK;
 }
 
+static int vec_group(int V) {  // lanes per row for the vectorised softmax kernels, 0 = use the generic path
+  if ((V & 3) != 0 || V > 128) return 0;
+  int g = 1;
+  while (g * 4 < V) g <<= 1;
+  return g;
+}
+
+#define EODM_SOFTMAX_DISPATCH(KERNEL, G, ...)                                                         \
+  do {                                                                                                \
+    const int64_t threads = rows * (G);                                                               \
+    const unsigned grid = (unsigned)((threads + 255) / 256);                                          \
+    switch (G) {                                                                                      \
+      case 1: KERNEL<1><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                    \
+      case 2: KERNEL<2><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                    \
+      case 4: KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                    \
+      case 8: KERNEL<8><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                    \
+      case 16: KERNEL<16><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                  \
+      default: KERNEL<32><<<grid, 256, 0, st>>>(__VA_ARGS__); break;                                  \
+    }                                                                                                 \
+  } while (0)
+
 int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st) {
   if (rows == 0) return EODM_OK;
+  const int G = vec_group(V);
+  if (G && (((uintptr_t)logits | (uintptr_t)px) & 15) == 0 && rows * G / 256 < 0x7fffffffLL) {
+    EODM_SOFTMAX_DISPATCH(eodm_softmax_fwd_vec_kernel, G, logits, rows, V, px);
+    EODM_CHECK_LAUNCH("eodm_softmax_fwd_vec_kernel");
+    return EODM_OK;
+  }
   const int wpb = 8;
   eodm_softmax_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(logits, rows, V, px);
   EODM_CHECK_LAUNCH("eodm_softmax_fwd_kernel");
@@ -158,6 +227,12 @@ int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px,
 
 int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st) {
   if (rows == 0) return EODM_OK;
+  const int G = vec_group(V);
+  if (G && (((uintptr_t)px | (uintptr_t)dpx | (uintptr_t)dlogits) & 15) == 0 && rows * G / 256 < 0x7fffffffLL) {
+    EODM_SOFTMAX_DISPATCH(eodm_softmax_bwd_vec_kernel, G, px, dpx, rows, V, dlogits);
+    EODM_CHECK_LAUNCH("eodm_softmax_bwd_vec_kernel");
+    return EODM_OK;
+  }
   const int wpb = 8;
   eodm_softmax_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(px, dpx, rows, V, dlogits);
   EODM_CHECK_LAUNCH("eodm_softmax_bwd_kernel");

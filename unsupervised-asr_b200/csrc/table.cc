@@ -311,8 +311,18 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
       node_z_all.push_back(-1);
       perm_all.insert(perm_all.end(), tb.perm.begin(), tb.perm.end());
     }
+    tr.roots = nullptr;
+    std::vector<EodmRoot> roots;
+    for (size_t u = 0; u < tb.units.size(); ++u) {
+      const uint32_t phone = tb.units[u].root_flags & 0xffffu, flags = tb.units[u].root_flags >> 16;
+      if (flags & EODM_UNIT_FIRST) roots.push_back(EodmRoot{phone, (uint32_t)u, 0u, 0u});
+      if (flags & EODM_UNIT_SELF) roots.back().n_self++;
+      roots.back().n_units++;
+    }
+    tr.n_roots = (int)roots.size();
     if (host_only) continue;
     if ((rc = upload(t, tb.units, &tr.units)) != EODM_OK) break;
+    if ((rc = upload(t, roots, &tr.roots)) != EODM_OK) break;
   }
   // slack for the kernels' line prefetch past the last trie
   nodes_all.insert(nodes_all.end(), 128, 0u);

@@ -39,11 +39,20 @@ struct EodmUnit {        // 16 bytes, read with one uniform 128-bit load
   uint32_t cost_before;  // prefix sum of unit costs (for splitting work between warps)
 };
 
+struct EodmRoot {       // 16 bytes: the units of one root phone are contiguous, those ending at the root first
+  uint32_t phone;
+  uint32_t first_unit;
+  uint32_t n_self;      // units that are an n-gram ending at the root itself
+  uint32_t n_units;     // all units of this root
+};
+
 struct EodmTrie {
   // device
   const uint32_t* nodes;
   const EodmUnit* units;
   const int32_t* perm;
+  const EodmRoot* roots;
+  int n_roots;
   // sizes
   int n_nodes, n_units, n_leaves;
   uint32_t total_cost;

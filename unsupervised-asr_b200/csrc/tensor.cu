@@ -32,12 +32,13 @@
 
 namespace {
 
-constexpr int kProd = 512;             // producer threads: 4 warpgroups, one M tile each
+constexpr int kProd = 512;             // warpgroups 0-2 produce A (one M tile each), warpgroup 3 produces B and stages px
 constexpr int kTThreads = kProd + 32;  // + the MMA-issuing warp
 constexpr int kKC = 8;                 // windows per chunk = K of one tf32 MMA
 constexpr int kSuper = 128;            // windows per staged px tile
 constexpr int kDR = kSuper / kKC;      // chunks per accumulation round (see "rounds" below)
-constexpr int kMaxMT = 4;              // M tiles per CTA
+constexpr int kMaxMT = 3;              // M tiles per CTA
+constexpr int kStages = 4;             // A (TMEM) and B (shared) stages
 constexpr uint32_t kTmemCols = 512;
 constexpr float kEps = 1e-15f;
 
@@ -51,7 +52,8 @@ struct TcFwdArgs {
 };
 
 struct TcBars {
-  uint64_t a_full[kMaxMT][2], a_free[kMaxMT][2], b_full[2], b_free[2], d_full[2], d_empty[2];
+  uint64_t a_full[kMaxMT][kStages], a_free[kMaxMT][kStages], b_full[kStages], b_free[kStages];
+  uint64_t d_full[2], d_empty[2], pt_full[2], pt_free[2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,21 +125,27 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory"); }
 
 // Rounds.  The tensor core adds every MMA's partial sum into the fp32 accumulator with truncation, so a long
 // accumulation chain drifts low (measured: -3.7e-8 relative per MMA; -3e-5 over a slice of 2000 windows).
 // The accumulators therefore live in TMEM for one round of kDR chunks only (48 MMAs per element), then are
 // added -- round-to-nearest -- to fp32 sums held in the producer threads' registers; two TMEM banks
 // alternate so the drain of one round overlaps the MMAs of the next.
+//
+// Roles.  Warpgroup g < MT: thread = TMEM lane = prefix row of M tile g; per chunk it forms Q for 8 windows,
+// splits it and writes A stage (g, s).  Warpgroup 3: the B operand of every chunk, and the next px tile
+// (global -> registers -> shared, one float4 per thread and chunk, so the copy never stalls a chunk).
+// Warp 16, one thread: waits for operands, issues the MMAs, commits stage-free / round-full barriers.
 template <int NP, int NPAD>  // prefix length n-1; V padded to a multiple of 16
 __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int V = a.V, n = a.n, VS = a.V + 1;            // px tile rows carry one extra, zero, column
+  constexpr int VS = NPAD + 1;                          // px tile row stride; columns V..NPAD stay zero
   constexpr int b_floats = NPAD * kKC;                  // one B operand (hi or lo) of one stage
-  float* Bs = reinterpret_cast<float*>(smem_raw);       // [2 stages][hi, lo][NPAD * 8]
-  float* wm = Bs + 4 * b_floats;                        // [kSuper]
-  float* Pt = wm + kSuper;                              // [kSuper + n - 1][V + 1]
+  const int V = a.V, n = a.n;
+  const int pt_floats = (kSuper + n - 1) * VS;
+  float* Bs = reinterpret_cast<float*>(smem_raw);       // [kStages][hi, lo][NPAD * 8]
+  float* wm = Bs + kStages * 2 * b_floats;              // [2][kSuper]
+  float* Pt = wm + 2 * kSuper;                          // [2][kSuper + n - 1][VS]
   __shared__ __align__(8) TcBars bars;
   __shared__ uint32_t tmem_slot;
 
@@ -155,18 +163,23 @@ __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_
   }
   if (tid == 0) {
     for (int g = 0; g < kMaxMT; ++g)
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < kStages; ++s) {
         mbar_init(&bars.a_full[g][s], 4);  // the four warps of the producing warpgroup
         mbar_init(&bars.a_free[g][s], 1);  // tcgen05.commit
       }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars.b_full[s], kProd / 32);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars.b_full[s], 4);
       mbar_init(&bars.b_free[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.d_full[s], 1);
       mbar_init(&bars.d_empty[s], 4 * MT);
+      mbar_init(&bars.pt_full[s], 4);
+      mbar_init(&bars.pt_free[s], 4 * MT);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < 2 * pt_floats; i += kTThreads) Pt[i] = 0.f;  // the zero columns (and everything else once)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -175,6 +188,7 @@ __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_
   const long long w_begin = (long long)slice * a.rows_per_slice;
   const long long w_end = (w_begin + a.rows_per_slice < a.NR) ? w_begin + a.rows_per_slice : a.NR;
   const int total_chunks = w_end > w_begin ? (int)((w_end - w_begin + kKC - 1) / kKC) : 0;
+  const int n_tiles = (total_chunks + kDR - 1) / kDR;
 
   if (warp == kProd / 32) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
       for (int i = 0; i < total_chunks; ++i) {
-        const int s = i & 1, use = i >> 1, r = i / kDR, bank = r & 1;
+        const int s = i % kStages, use = i / kStages, r = i / kDR, bank = r & 1;
         const bool first = (i % kDR) == 0;
         if (first && r >= 2) mbar_wait(&bars.d_empty[bank], (uint32_t)(((r >> 1) - 1) & 1));
         mbar_wait(&bars.b_full[s], (uint32_t)(use & 1));
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_
           mbar_wait(&bars.a_full[g][s], (uint32_t)(use & 1));
           tc_fence_after();
           const uint32_t d = tmem + (uint32_t)((bank * a.MT + g) * NPAD);
-          const uint32_t ahi = tmem + colA0 + (uint32_t)((g * 2 + s) * 16), alo = ahi + 8;
+          const uint32_t ahi = tmem + colA0 + (uint32_t)((g * kStages + s) * 16), alo = ahi + 8;
           mma_tf32_ts(d, ahi, dhi, idesc, first ? 0u : 1u);
           mma_tf32_ts(d, alo, dhi, idesc, 1u);
           mma_tf32_ts(d, ahi, dlo, idesc, 1u);
@@ -203,103 +217,182 @@ __global__ void __launch_bounds__(kTThreads, 1) eodm_tc_fwd_kernel(const __grid_
         if ((i % kDR) == kDR - 1 || i == total_chunks - 1) mma_commit(&bars.d_full[bank]);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ producers
-    const bool active = wg < MT;  // warpgroup wg owns M tile wg of this CTA's group
-    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    const int row = (mg * a.MT + wg) * 128 + l128;
-    int tok[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) tok[j] = (active && row < a.n_rows) ? __ldg(a.tok + (size_t)row * NP + j) : V;
-    float acc[NPAD];
-#pragma unroll
-    for (int k = 0; k < NPAD; ++k) acc[k] = 0.f;
-
-    auto drain = [&](int r) {  // add round r's TMEM accumulators into the register sums
-      const int bank = r & 1;
-      mbar_wait(&bars.d_full[bank], (uint32_t)((r >> 1) & 1));
-      tc_fence_after();
-#pragma unroll
-      for (int cg = 0; cg < NPAD; cg += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + lane_field + (uint32_t)((bank * a.MT + wg) * NPAD + cg), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[cg + k] += __uint_as_float(v[k]);
+  } else if (wg == 3) {
+    // ------------------------------------------------------------------ B operand + px staging
+    const bool vec = (V & 3) == 0;
+    const int per_row = vec ? (V >> 2) : V;                    // staged units (float4 or float) per px row
+    const int units = (kSuper + n - 1) * per_row;
+    const int upc = (units + kDR * 128 - 1) / (kDR * 128);    // units per thread and chunk
+    auto stage_load = [&](long long st0, int u, float4& v) {
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < units) {
+        const int rr = u / per_row;
+        if (st0 + rr < a.NR) {
+          if (vec) v = __ldg(reinterpret_cast<const float4*>(a.px + st0 * V) + u);
+          else v.x = __ldg(a.px + st0 * V + u);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.d_empty[bank]);
     };
-
-    int i = 0;
-    for (long long st0 = w_begin; st0 < w_end; st0 += kSuper) {
-      bar_sync_producers();  // every reader of the previous px tile is done
-      {
-        const int nrows = kSuper + n - 1;
-        for (int idx = tid; idx < nrows * VS; idx += kProd) {
-          const int rr = idx / VS, cc = idx - rr * VS;
-          const long long gr = st0 + rr;
-          Pt[idx] = (cc < V && gr < a.NR) ? __ldg(a.px + gr * V + cc) + kEps : 0.f;
-        }
-        if (tid < kSuper) {
-          const long long wrow = st0 + tid;
-          float ok = 0.f;
-          if (wrow < w_end) {
-            const int t = (int)(wrow % a.T);
-            ok = (t <= a.T - n && __ldg(a.mask + wrow) != 0) ? 1.f : 0.f;
-          }
-          wm[tid] = ok;
+    auto stage_store = [&](float* P, long long st0, int u, const float4& v) {
+      if (u < units) {
+        const int rr = u / per_row, cc = u - rr * per_row;
+        const bool in = st0 + rr < a.NR;
+        if (vec) {
+          float* d = P + rr * VS + cc * 4;
+          d[0] = in ? v.x + kEps : 0.f; d[1] = in ? v.y + kEps : 0.f;
+          d[2] = in ? v.z + kEps : 0.f; d[3] = in ? v.w + kEps : 0.f;
+        } else {
+          P[rr * VS + cc] = in ? v.x + kEps : 0.f;
         }
       }
-      bar_sync_producers();
-      const long long left = w_end - st0;
-      const int nchunks = (int)(((left < kSuper ? left : kSuper) + kKC - 1) / kKC);
+    };
+    auto stage_mask = [&](float* wmb, long long st0) {
+      const long long wrow = st0 + l128;
+      float ok = 0.f;
+      if (wrow < w_end) {
+        const int t = (int)(wrow % a.T);
+        ok = (t <= a.T - n && __ldg(a.mask + wrow) != 0) ? 1.f : 0.f;
+      }
+      wmb[l128] = ok;
+    };
+    // first tile: all at once
+    if (n_tiles > 0) {
+      for (int u = l128; u < units; u += 128) {
+        float4 v;
+        stage_load(w_begin, u, v);
+        stage_store(Pt, w_begin, u, v);
+      }
+      stage_mask(wm, w_begin);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.pt_full[0]);
+    }
+    int i = 0;
+    for (int k = 0; k < n_tiles; ++k) {
+      const int buf = k & 1;
+      const long long st0 = w_begin + (long long)k * kSuper;
+      const bool has_next = k + 1 < n_tiles;
+      float* Pcur = Pt + buf * pt_floats;
+      float* Pnext = Pt + (buf ^ 1) * pt_floats;
+      const float* wmc = wm + buf * kSuper;
+      mbar_wait(&bars.pt_full[buf], (uint32_t)((k >> 1) & 1));  // the other staging threads' stores
+      bool next_free = !(has_next && k >= 1);  // the A producers may still be reading the other buffer (tile k-1)
+      const int nchunks = min(kDR, total_chunks - k * kDR);
+      float4 held[4];
+      int held_c = -1;
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c, ++i) {
-        const int s = i & 1, use = i >> 1;
+        const int s = i % kStages, use = i / kStages;
         const int w0 = c * kKC;
-        if (active) {
+        // issue this chunk's share of the next tile's loads; store the previous chunk's
+        float4 cur[4];
+        if (has_next) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < upc) stage_load(st0 + kSuper, (c * upc + q) * 128 + l128, cur[q]);
+        }
+        if (use > 0) mbar_wait(&bars.b_free[s], (uint32_t)((use - 1) & 1));
+        float* Bhi = Bs + (2 * s) * b_floats;
+        for (int e = l128; e < b_floats; e += 128) {
+          const int cc = e >> 3, w = e & 7;
+          const float v = Pcur[(w0 + w + n - 1) * VS + cc] * wmc[w0 + w];  // columns >= V are zero
+          uint32_t hi, lo;
+          split_tf32(v, hi, lo);
+          const int off = (w >> 2) * (NPAD * 4) + (cc >> 3) * 32 + (cc & 7) * 4 + (w & 3);
+          Bhi[off] = __uint_as_float(hi);
+          Bhi[b_floats + off] = __uint_as_float(lo);
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.b_full[s]);
+        if (has_next) {
+          if (held_c >= 0) {
+            if (!next_free) {
+              mbar_wait(&bars.pt_free[buf ^ 1], (uint32_t)((((k + 1) >> 1) - 1) & 1));
+              next_free = true;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < upc) stage_store(Pnext, st0 + kSuper, (held_c * upc + q) * 128 + l128, held[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) held[q] = cur[q];
+          held_c = c;
+        }
+      }
+      if (has_next) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < upc) stage_store(Pnext, st0 + kSuper, (held_c * upc + q) * 128 + l128, held[q]);
+        stage_mask(wm + (buf ^ 1) * kSuper, st0 + kSuper);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.pt_full[buf ^ 1]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ A producers
+    const bool active = wg < MT;  // warpgroup wg owns M tile wg of this CTA's group
+    if (active) {
+      const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+      const int row = (mg * a.MT + wg) * 128 + l128;
+      int tok[NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) tok[j] = (row < a.n_rows) ? __ldg(a.tok + (size_t)row * NP + j) : V;
+      float acc[NPAD];
+#pragma unroll
+      for (int k = 0; k < NPAD; ++k) acc[k] = 0.f;
+
+      auto drain = [&](int r) {  // add round r's TMEM accumulators into the register sums
+        const int bank = r & 1;
+        mbar_wait(&bars.d_full[bank], (uint32_t)((r >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int cg = 0; cg < NPAD; cg += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_field + (uint32_t)((bank * a.MT + wg) * NPAD + cg), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc[cg + k] += __uint_as_float(v[k]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.d_empty[bank]);
+      };
+
+      int i = 0;
+      for (int k = 0; k < n_tiles; ++k) {
+        const int buf = k & 1;
+        mbar_wait(&bars.pt_full[buf], (uint32_t)((k >> 1) & 1));
+        const float* tp[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) tp[j] = Pt + buf * pt_floats + j * VS + tok[j];
+        const int nchunks = min(kDR, total_chunks - k * kDR);
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c, ++i) {
+          const int s = i % kStages, use = i / kStages;
           if (use > 0) {
             mbar_wait(&bars.a_free[wg][s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage are done
             tc_fence_after();
           }
           uint32_t r[16];
-          const float* cb = Pt + w0 * VS;
+          const int cb = c * kKC * VS;
 #pragma unroll
           for (int w = 0; w < kKC; ++w) {
-            float q = cb[w * VS + tok[0]];  // dead rows read the zero column
+            float q = tp[0][cb + w * VS];  // dead rows read the zero column
 #pragma unroll
-            for (int j = 1; j < NP; ++j) q *= cb[(w + j) * VS + tok[j]];
+            for (int j = 1; j < NP; ++j) q *= tp[j][cb + w * VS];
             split_tf32(q, r[w], r[8 + w]);
           }
-          tmem_st16(tmem + lane_field + colA0 + (uint32_t)((wg * 2 + s) * 16), r);
+          tmem_st16(tmem + lane_field + colA0 + (uint32_t)((wg * kStages + s) * 16), r);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.a_full[wg][s]);
-        }
-        // this thread's share of the B operand: 8 windows x NPAD phones, masked, hi and lo
-        if (use > 0) mbar_wait(&bars.b_free[s], (uint32_t)((use - 1) & 1));
-        if (tid < b_floats) {
-          const int cc = tid >> 3, w = tid & 7;
-          float v = 0.f;
-          if (cc < V) v = Pt[(w0 + w + n - 1) * VS + cc] * wm[w0 + w];
-          uint32_t hi, lo;
-          split_tf32(v, hi, lo);
-          const int off = (w >> 2) * (NPAD * 4) + (cc >> 3) * 32 + (cc & 7) * 4 + (w & 3);
-          float* Bhi = Bs + (2 * s) * b_floats;
-          Bhi[off] = __uint_as_float(hi);
-          Bhi[b_floats + off] = __uint_as_float(lo);
-          fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+          // the previous round's accumulators, once this round's first chunk is on its way
+          if (i > 0 && (i % kDR) == 0) drain(i / kDR - 1);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.b_full[s]);
-        // the previous round's accumulators, once this round's first chunk is on its way
-        if (active && i > 0 && (i % kDR) == 0) drain(i / kDR - 1);
+        if (lane == 0) mbar_arrive(&bars.pt_free[buf]);
       }
-    }
-    if (active) {
       if (i > 0) drain((i - 1) / kDR);
       float* out = a.partS + ((size_t)slice * a.n_mtiles * 128 + row) * NPAD;
 #pragma unroll
@@ -352,7 +445,7 @@ bool tc_plan(const eodm_table* t, long long NR, TcPlan* p) {
   const int j = t->n - 1;
   const int Npad = (t->V + 15) & ~15;
   if (Npad > 64) return false;  // one register accumulator per padded phone and producer thread
-  int mt_max = 512 / (2 * Npad + 32);
+  int mt_max = 512 / (2 * Npad + 16 * kStages);
   if (mt_max > kMaxMT) mt_max = kMaxMT;
   const int n_mtiles = (t->rows[j].n_rows + 127) / 128;
   const int G_m = (n_mtiles + mt_max - 1) / mt_max;
@@ -368,7 +461,7 @@ bool tc_plan(const eodm_table* t, long long NR, TcPlan* p) {
   n_slices = (int)((NR + rps - 1) / rps);
   p->n_slices = n_slices;
   p->rows_per_slice = rps;
-  p->smem = sizeof(float) * ((size_t)4 * Npad * kKC + kSuper + (size_t)(kSuper + t->n - 1) * (t->V + 1)) + 128;
+  p->smem = sizeof(float) * ((size_t)kStages * 2 * Npad * kKC + 2 * kSuper + (size_t)2 * (kSuper + t->n - 1) * (Npad + 1)) + 128;
   p->part_bytes = sizeof(float) * (size_t)n_slices * n_mtiles * 128 * Npad;
   return p->smem <= 200 * 1024;
 }
