@@ -302,3 +302,27 @@ def synth_batch(B, T, V, seed=1234, scale=2.0, len_lo=None):
         lens = rng.integers(len_lo, T + 1, size=B)
     mask = np.arange(T)[None, :] < lens[:, None]
     return logits, mask
+
+
+# --------------------------------------------------------------------------
+# dense bigram contraction (all V*V bigrams at once; BASELINE config 4)
+# --------------------------------------------------------------------------
+def bigram_dense_fwd(px, mask, dtype=np.float64):
+    """C[u,v] = sum_{b, t<=T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps): the counts S of counts_fwd for the
+    table of ALL bigrams (z = u*V + v), i.e. models/EODM.py:18-19 with a kernel_size-2 one-hot kernel per pair."""
+    P = np.asarray(px, dtype=dtype) + dtype(EPS)
+    m = np.asarray(mask).astype(dtype)[:, :-1]
+    B, T, V = P.shape
+    A = (P[:, :-1] * m[:, :, None]).reshape(-1, V)
+    return A.T @ P[:, 1:].reshape(-1, V), dtype(np.asarray(mask).sum())
+
+
+def bigram_dense_bwd(px, mask, G, dtype=np.float64):
+    """dpx for upstream G = dloss/dC."""
+    P = np.asarray(px, dtype=dtype) + dtype(EPS)
+    m = np.asarray(mask).astype(dtype)[:, :-1, None]
+    G = np.asarray(G, dtype=dtype)
+    d = np.zeros_like(P)
+    d[:, :-1] += m * (P[:, 1:] @ G.T)
+    d[:, 1:] += (m * P[:, :-1]) @ G
+    return d

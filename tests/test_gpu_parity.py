@@ -215,7 +215,7 @@ def test_softmax_kernels(eodm):
         x = torch.randn(37, 5, V, device=dev) * 5
         px = eodm.softmax_fwd(x)
         ref = torch.softmax(x.double(), -1)
-        assert float(((px.double() - ref).abs() / ref).max()) <= 2e-6, V
+        assert float(((px.double() - ref).abs() / ref).max()) <= 5e-6, V      # expf: ~|x| ulp on far-tail entries
         d = torch.randn_like(px)
         ref = px.double() * (d.double() - (px.double() * d.double()).sum(-1, keepdim=True))
         got = eodm.softmax_bwd(px, d).double()
@@ -305,3 +305,41 @@ def test_full_size_properties(eodm):
     # sampled rows of the gradient against the oracle restricted to one utterance (windows do not cross utterances)
     d_ref = O.counts_bwd(pxh[3:4] - 1e-15, w["mask"][3:4], w["ids"], n, g1.cpu().numpy().astype(np.float64))
     assert rel_max(d1[3:4].cpu().numpy(), d_ref) <= TOL
+
+
+@pytest.mark.parametrize("B,T,V,ragged", [(2, 9, 128, False), (3, 40, 256, True), (4, 33, 384, True), (6, 50, 1024, True)])
+def test_dense_bigram_tcgen05_vs_oracle(eodm, B, T, V, ragged):
+    """eodm_bigram_dense_fwd/bwd (tcgen05, 3xTF32, TMEM accumulators drained every 16 K-steps) vs the fp64 oracle."""
+    dev = _dev()
+    logits, mask = O.synth_batch(B, T, V, seed=B, len_lo=2 if ragged else None, scale=3.0)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    px64 = px.cpu().numpy().astype(np.float64)
+    m = torch.tensor(mask, device=dev)
+    Cm, N = eodm.bigram_dense_fwd(px, m)
+    C_ref, N_ref = O.bigram_dense_fwd(px64, mask)
+    assert float(N) == N_ref
+    assert rel_max(Cm.cpu().numpy(), C_ref) <= TOL
+    G = np.random.default_rng(0).standard_normal((V, V)).astype(np.float32)
+    d = eodm.bigram_dense_bwd(px, m, torch.tensor(G, device=dev)).cpu().numpy()
+    d_ref = O.bigram_dense_bwd(px64, mask, G.astype(np.float64))
+    assert rel_max(d, d_ref) <= TOL and rel_l2(d, d_ref) <= TOL
+    # bit-reproducible
+    assert torch.equal(Cm, eodm.bigram_dense_fwd(px, m)[0])
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.bigram_dense_fwd(px[:, :, :100].contiguous(), m)       # V not a multiple of 128
+    assert e.value.status == -5
+
+
+def test_dense_bigram_agrees_with_table_path(eodm):
+    """The same counts through the trie walk with the table of a bigram subset."""
+    dev = _dev()
+    V, B, T = 128, 3, 30
+    logits, mask = O.synth_batch(B, T, V, seed=9, len_lo=5)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    m = torch.tensor(mask, device=dev)
+    ids, py = eodm.synth.table(V, 2, 3000, seed=9, min_id=0)
+    counts = eodm.counts_fwd(eodm.NgramTable.from_ids(ids, V, device=0), px, m)
+    Cm, N = eodm.bigram_dense_fwd(px, m)
+    sel = Cm[torch.tensor(ids[:, 0].astype(np.int64), device=dev), torch.tensor(ids[:, 1].astype(np.int64), device=dev)]
+    assert float(((sel - counts[:3000]).abs() / counts[:3000]).max()) <= TOL
+    assert float(N) == float(counts[3000])

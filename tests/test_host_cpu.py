@@ -103,6 +103,19 @@ def test_oracle_finite_differences():
         assert abs(fd - r["dlogits"][b, t, v]) < 1e-6 * max(1.0, abs(fd))
 
 
+def test_oracle_dense_bigram_equals_table_of_all_bigrams():
+    rng = np.random.default_rng(4)
+    V, B, T = 6, 3, 7
+    ids = np.array([[u, v] for u in range(V) for v in range(V)], np.int32)
+    logits, mask = O.synth_batch(B, T, V, seed=4, len_lo=1)
+    px = O.softmax(logits)
+    S, N = O.counts_fwd(px, mask, ids, 2)
+    Cm, N2 = O.bigram_dense_fwd(px, mask)
+    assert N == N2 and np.allclose(Cm.reshape(-1), S, rtol=1e-13, atol=0)
+    G = rng.standard_normal((V, V))
+    assert np.allclose(O.bigram_dense_bwd(px, mask, G), O.counts_bwd(px, mask, ids, 2, G.reshape(-1)), rtol=1e-12, atol=1e-300)
+
+
 # ---------------------------------------------------------------- product host logic
 def test_tools_match_oracle_and_golden(eodm, golden, tmp_path):
     # a small n-gram file in the reference's format, including the unigram parse quirk

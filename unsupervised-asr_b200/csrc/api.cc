@@ -214,21 +214,6 @@ extern "C" int eodm_allreduce_counts(void* comm, float* S, int K, float* N, void
 }
 
 // ---------------------------------------------------------------------------
-// dense bigram path (tcgen05): built in bigram.cu when present
-// ---------------------------------------------------------------------------
-#ifndef EODM_HAVE_BIGRAM
-extern "C" size_t eodm_bigram_workspace_bytes(int, int, int) { return 0; }
-extern "C" int eodm_bigram_dense_fwd(const float*, const uint8_t*, int, int, int, float*, float*, void*, void*) {
-  eodm_set_error("dense bigram path is not part of this build");
-  return EODM_EUNSUPPORTED;
-}
-extern "C" int eodm_bigram_dense_bwd(const float*, const uint8_t*, int, int, int, const float*, float*, void*, void*) {
-  eodm_set_error("dense bigram path is not part of this build");
-  return EODM_EUNSUPPORTED;
-}
-#endif
-
-// ---------------------------------------------------------------------------
 // session: EODM_loss forward + gradient wrt logits in one call
 // ---------------------------------------------------------------------------
 struct eodm_session {

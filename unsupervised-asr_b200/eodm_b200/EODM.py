@@ -313,3 +313,33 @@ def EODM_loss(_logits, mask, conv_op, k, py):
                         (_logits.shape[1] if _logits.dim() == 3 else "?", table.n))
     mask_u8 = _mask_u8(mask, _logits.device)
     return _EodmLossFn.apply(_logits, mask_u8, py, table, conv_op.comm)
+
+
+# ---------------------------------------------------------------------------
+# dense bigram contraction for large vocabularies (tcgen05 path)
+# ---------------------------------------------------------------------------
+def bigram_dense_fwd(px, mask):
+    """C[u, v] = sum_{b, t<=T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps), f32[V, V]; N = sum(mask).
+    V must be a multiple of 128."""
+    px = _f32c(px, "px")
+    B, T, V = px.shape
+    mask = _mask_u8(mask, px.device)
+    Cm = torch.empty((V, V), dtype=torch.float32, device=px.device)
+    N = torch.empty(1, dtype=torch.float32, device=px.device)
+    ws = torch.empty(max(lib.eodm_bigram_workspace_bytes(B, T, V), 256), dtype=torch.uint8, device=px.device)
+    check(lib.eodm_bigram_dense_fwd(_ptr(px), _ptr(mask), B, T, V, _ptr(Cm), _ptr(N), _ptr(ws), _stream()))
+    return Cm, N
+
+
+def bigram_dense_bwd(px, mask, G):
+    """dpx f32[B, T, V] for an upstream G = dloss/dC f32[V, V]."""
+    px = _f32c(px, "px")
+    B, T, V = px.shape
+    mask = _mask_u8(mask, px.device)
+    G = _f32c(G, "G")
+    if tuple(G.shape) != (V, V):
+        raise EodmError(_lib.ESHAPE, "G must be [%d, %d], got %r" % (V, V, tuple(G.shape)))
+    dpx = torch.empty_like(px)
+    ws = torch.empty(max(lib.eodm_bigram_workspace_bytes(B, T, V), 256), dtype=torch.uint8, device=px.device)
+    check(lib.eodm_bigram_dense_bwd(_ptr(px), _ptr(mask), B, T, V, _ptr(G), _ptr(dpx), _ptr(ws), _stream()))
+    return dpx

@@ -6,6 +6,6 @@ Importing this package loads libeodm_b200.so (built in-tree by
 from ._lib import EodmError, LIB_PATH, lib  # noqa: F401
 from .tools import load_vocab, read_ngram, ngram2kernel, ngram_ids  # noqa: F401
 from .EODM import (P_Ngram, EODM_loss, PNgram, NgramTable, softmax_fwd, softmax_bwd, counts_fwd, counts_bwd,  # noqa: F401
-                   loss_from_counts)
+                   loss_from_counts, bigram_dense_fwd, bigram_dense_bwd)
 from .session import Session  # noqa: F401
 from . import dist, synth  # noqa: F401
