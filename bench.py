@@ -268,6 +268,21 @@ def main():
                 "achieved_gbs": 12.0 * B * T * V / (t_f + t_b) / 1e9},
     }
     roofline["path_fwd_bwd"]["frac"] = roofline["path_fwd_bwd"]["roofline_ms"] / roofline["path_fwd_bwd"]["ms"]
+    try:  # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.workload == "timit_c2":
+            roofline["traffic"] = traffic.get(roofline["kernel"])
+    except Exception:
+        pass
+    # the resource that actually binds the sparse walk: one shared-memory wavefront per (trie node, 32 windows);
+    # 0.90 wavefronts/clk/SM measured with tools/ubench.cu on this pool (profiles/r01_ubench.txt)
+    rows32 = (B * T + 31) // 32
+    wf_f, wf_b = float(table.fwd_nodes) * rows32, float(table.bwd_nodes) * rows32
+    lds_peak = 0.90 * n_sm * sm_max * 1e6
+    roofline["smem_wavefronts"] = {
+        "fwd": {"algorithmic": wf_f, "floor_ms": wf_f / lds_peak * 1e3, "frac": wf_f / lds_peak / t_f},
+        "bwd": {"algorithmic": wf_b, "floor_ms": wf_b / lds_peak * 1e3, "frac": wf_b / lds_peak / t_b},
+        "peak_wavefronts_per_clk_per_sm": 0.90, "note": "measured LDS.32 rate; the walk's binding resource"}
 
     # ---- end to end through the host-buffer session (H2D + D2H inside the timed region) ----
     e2e = None
@@ -307,7 +322,7 @@ def main():
             "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
                        "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
-                       "path": "cuda-core trie walk (v1)"},
+                       "path": "cuda-core trie walk (v2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }

@@ -179,6 +179,40 @@ struct FwdWalk {
 template <int L, int DEPTH, int R>
 __device__ __forceinline__ void fwd_visit(FwdWalk& w, const TrieArg& tr, const float* Pl, int ld, const float (&qp)[R],
                                           int count) {
+  if constexpr (L + 1 == DEPTH) {
+    // deepest level: every node ends an n-gram.  Two per trip with the loads up front (see bwd_visit).
+    const float* base = Pl + tr.off[L];
+    int c = 0;
+#pragma unroll 1
+    for (; c + 2 <= count; c += 2) {
+      const uint32_t e0 = w.next();
+      const uint32_t e1 = w.next();
+      const float* r0 = base + EODM_NODE_PHONE(e0) * ld;
+      const float* r1 = base + EODM_NODE_PHONE(e1) * ld;
+      float a0[R], a1[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a0[r] = r0[32 * r];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a1[r] = r1[32 * r];
+      float s0 = qp[0] * a0[0], s1 = qp[0] * a1[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        s0 = fmaf(qp[r], a0[r], s0);
+        s1 = fmaf(qp[r], a1[r], s1);
+      }
+      w.emit(s0);
+      w.emit(s1);
+    }
+    if (c < count) {
+      const uint32_t e = w.next();
+      const float* row = base + EODM_NODE_PHONE(e) * ld;
+      float s = qp[0] * row[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) s = fmaf(qp[r], row[32 * r], s);
+      w.emit(s);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c = 0; c < count; ++c) {
     const uint32_t e = w.next();
@@ -352,6 +386,37 @@ struct BwdWalk {
 template <int L, int DEPTH, int R>
 __device__ __forceinline__ void bwd_visit(BwdWalk& w, const TrieArg& tr, const float* Pl, int ld, float (&out)[R],
                                           int count) {
+  if constexpr (L + 1 == DEPTH) {
+    // deepest level: nothing but n-gram ends.  Two per trip, all loads before the FMAs, so that a warp keeps
+    // 2R shared-memory reads in flight (the walk is bound by shared-memory wavefronts, not by issue).
+    const float* base = Pl + tr.off[L];
+    int c = 0;
+#pragma unroll 1
+    for (; c + 2 <= count; c += 2) {
+      const uint2 e0 = w.next();
+      const uint2 e1 = w.next();
+      const float* r0 = base + EODM_NODE_PHONE(e0.x) * ld;
+      const float* r1 = base + EODM_NODE_PHONE(e1.x) * ld;
+      float a0[R], a1[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a0[r] = r0[32 * r];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a1[r] = r1[32 * r];
+      const float g0 = __uint_as_float(e0.y), g1 = __uint_as_float(e1.y);
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = fmaf(a0[r], g0, out[r]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = fmaf(a1[r], g1, out[r]);
+    }
+    if (c < count) {
+      const uint2 e = w.next();
+      const float g = __uint_as_float(e.y);
+      const float* row = base + EODM_NODE_PHONE(e.x) * ld;
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, out[r]);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c = 0; c < count; ++c) {
     const uint2 e = w.next();
