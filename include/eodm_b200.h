@@ -99,6 +99,27 @@ int eodm_loss_from_counts(const float* S, const float* N, const float* py, int K
 int eodm_softmax_fwd(const float* logits, int64_t rows, int V, float* px, void* stream);
 int eodm_softmax_bwd(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, void* stream);
 
+/* ---- the steps either side of the path inside train_step (main_EODM.py:158-182) ---- */
+/* px[b][l][:] = softmax(logits[b][idx[b][l]][:]): tf.gather_nd (main_EODM.py:163, indices from stamps2indices,
+ * utils/tools.py:465-485) fused with the softmax of models/EODM.py:15.  logits f32[B][T][V], idx int32[B][L]
+ * (frame index per slot; padded slots carry 0 and gather frame 0, as in the reference), px f32[B][L][V]. */
+int eodm_gather_softmax_fwd(const float* logits, const int32_t* idx, int B, int T, int L, int V, float* px,
+                            void* stream);
+/* VJP: dlogits f32[B][T][V] (overwritten; frames no slot gathered get zeros, slots sharing a frame add up). */
+int eodm_gather_softmax_bwd(const float* px, const float* dpx, const int32_t* idx, int B, int T, int L, int V,
+                            float* dlogits, void* stream);
+/* CE_loss (utils/tools.py:538-557): label-smoothed softmax cross-entropy minus its entropy floor, mean over
+ * labels > 0.  logits f32[rows][V], labels int32[rows]; loss f32[1]; dlogits f32[rows][V] or NULL. */
+size_t eodm_ce_loss_workspace_bytes(int64_t rows);
+int eodm_ce_loss(const float* logits, const int32_t* labels, int64_t rows, int V, float confidence, float* loss,
+                 float* dlogits, void* ws, void* stream);
+/* frames_constrain_loss (utils/tools.py:419-434): sum over frames 2 <= i < max(align)+1 that are not a
+ * boundary (boundaries = align + 1) of mean_v (p[i-1][v] - p[i][v])^2, p = softmax(logits).  align int32[B][L] is
+ * read, not incremented (the reference mutates its argument).  loss f32[1]; dlogits f32[B][T][V] or NULL. */
+size_t eodm_frames_constrain_workspace_bytes(int B, int T, int V);
+int eodm_frames_constrain_loss(const float* logits, const int32_t* align, int B, int T, int L, int V, float* loss,
+                               float* dlogits, void* ws, void* stream);
+
 /* ---- materialising op: P_Ngram.__call__ (models/EODM.py:63-71) ---- */
 /* p[b,t,z] = prod_j (px[b,t+j,ids[z,j]] + 1e-15),  p f32[B][T-n+1][K]. */
 int eodm_prob_fwd(const eodm_table* t, const float* px, int B, int T, float* p, void* stream);

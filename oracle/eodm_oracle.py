@@ -326,3 +326,70 @@ def bigram_dense_bwd(px, mask, G, dtype=np.float64):
     d[:, :-1] += m * (P[:, 1:] @ G.T)
     d[:, 1:] += (m * P[:, :-1]) @ G
     return d
+
+
+# --------------------------------------------------------------------------
+# the steps either side of the path
+# --------------------------------------------------------------------------
+def ce_loss(logits, labels, vocab_size, confidence=0.9, dtype=np.float64):
+    """utils/tools.py:538-557 (CE_loss): label-smoothed softmax cross-entropy minus its
+    entropy floor, mean over labels > 0.  Returns (loss, dloss/dlogits)."""
+    x = np.asarray(logits, dtype=dtype)
+    labels = np.asarray(labels)
+    V = vocab_size
+    mask = (labels > 0).astype(dtype)
+    low = (1.0 - confidence) / dtype(V - 1)
+    normalizing = -(confidence * np.log(dtype(confidence)) + dtype(V - 1) * low * np.log(low + 1e-20))
+    soft = np.full(x.shape, low, dtype=dtype)
+    ok = (labels >= 0) & (labels < V)
+    bi, ti = np.nonzero(ok)
+    soft[bi, ti, labels[bi, ti]] = confidence
+    z = x - x.max(-1, keepdims=True)
+    lsm = z - np.log(np.exp(z).sum(-1, keepdims=True))
+    xent = -(soft * lsm).sum(-1)
+    n = mask.sum()
+    loss = ((xent - normalizing) * mask).sum() / n
+    dlogits = (np.exp(lsm) * soft.sum(-1, keepdims=True) - soft) * (mask / n)[..., None]
+    return dtype(loss), dlogits
+
+
+def frames_constrain_loss(logits, align, dtype=np.float64):
+    """utils/tools.py:419-434: sum over frames i >= 2 that are before the last boundary and are not a
+    boundary themselves (boundaries = align + 1) of mean_v (p[i-1,v] - p[i,v])^2.  `align` is NOT mutated here
+    (the reference increments the caller's array in place).  Returns (loss, dloss/dlogits)."""
+    x = np.asarray(logits, dtype=dtype)
+    B, T, V = x.shape
+    bound = np.asarray(align).astype(np.int64) + 1
+    end_time = bound.max(-1)
+    p = softmax(x, dtype)
+    gate = np.zeros((B, T), dtype=dtype)
+    for b in range(B):
+        for i in range(2, T):
+            gate[b, i] = float(i < end_time[b] and not np.any(bound[b] == i))
+    d = np.zeros_like(p)
+    d[:, 1:] = p[:, :-1] - p[:, 1:]                       # d[i] = p[i-1] - p[i]
+    loss = (gate * (d ** 2).mean(-1)).sum()
+    dp = np.zeros_like(p)
+    gd = gate[..., None] * d * (2.0 / V)
+    dp -= gd                                               # d/dp[i]
+    dp[:, :-1] += gd[:, 1:]                                # d/dp[i-1]
+    return dtype(loss), softmax_vjp(p, dp)
+
+
+def gather_softmax(logits, idx, dtype=np.float64):
+    """main_EODM.py:163 + models/EODM.py:15: px[b,l,:] = softmax(logits[b, idx[b,l], :])."""
+    x = np.asarray(logits, dtype=dtype)
+    B = x.shape[0]
+    return softmax(x[np.arange(B)[:, None], np.asarray(idx)], dtype)
+
+
+def gather_softmax_vjp(logits, idx, dpx, dtype=np.float64):
+    """dloss/dlogits[b,t,:] = sum_{l: idx[b,l]=t} softmax VJP (padded slots all gather frame 0 and add up there)."""
+    x = np.asarray(logits, dtype=dtype)
+    px = gather_softmax(x, idx, dtype)
+    dl = softmax_vjp(px, np.asarray(dpx, dtype=dtype))
+    out = np.zeros_like(x)
+    B, L = np.asarray(idx).shape
+    for b in range(B):
+        np.add.at(out[b], np.asarray(idx)[b], dl[b])
+    return out

@@ -101,8 +101,26 @@ def make_tf_shim():
     tf.cast = lambda x, dtype: x.to(dtype)
     tf.exp = _lift(torch.exp)
     tf.reduce_sum = lambda x, axis=None: x.sum() if axis is None else x.sum(dim=tuple(axis))
-    tf.nn = types.SimpleNamespace(softmax=lambda x: torch.softmax(x, -1))
-    tf.math = types.SimpleNamespace(log=_lift(torch.log))
+    def _sce(logits, labels):
+        return -(labels * torch.log_softmax(logits, -1)).sum(-1)
+
+    def _one_hot(labels, depth, on_value, off_value):
+        oh = torch.nn.functional.one_hot(labels.clamp(0, depth - 1).long(), depth).to(torch.float64)
+        oh = oh * ((labels >= 0) & (labels < depth)).to(torch.float64)[..., None]      # out-of-range -> all off
+        return (oh * on_value + (1 - oh) * off_value)
+
+    tf.nn = types.SimpleNamespace(softmax=lambda x: torch.softmax(x, -1), softmax_cross_entropy_with_logits=_sce)
+    tf.math = types.SimpleNamespace(log=_lift(lambda x: torch.log(torch.as_tensor(x, dtype=torch.float64)) if not isinstance(x, torch.Tensor) else torch.log(x)))
+    tf.int32 = torch.int32
+    tf.one_hot = lambda labels, depth, on_value, off_value: _one_hot(labels, depth, on_value, off_value)
+    tf.reduce_max = lambda x, axis=None: x.max() if axis is None else x.max(dim=axis).values
+    tf.reduce_mean = lambda x, axis=None: x.mean() if axis is None else x.mean(dim=axis)
+    tf.zeros = lambda shape, dtype=None: torch.zeros(*shape, dtype=torch.float64)
+    tf.unstack = lambda x, axis=0: list(torch.unbind(x, dim=axis))
+    tf.less = lambda a, b: torch.as_tensor(a) < b
+    tf.not_equal = lambda a, b: a != b
+    tf.logical_and = lambda a, b: a & b
+    tf.pow = lambda x, p: x ** p
     layers = types.ModuleType("tensorflow.keras.layers")
     layers.Input = lambda shape, name=None: Sym(lambda x: x)
     layers.Conv1D = _Conv1D
@@ -110,6 +128,7 @@ def make_tf_shim():
         setattr(layers, n, object)
     keras = _ShimModule("tensorflow.keras")
     keras.layers, keras.Model = layers, _Model
+    keras.backend = types.SimpleNamespace(all=lambda x, axis=None: x.all(dim=axis))
     tf.keras = keras
     return tf, keras, layers
 
@@ -227,6 +246,36 @@ def main():
     kernel_c, py_c = tools.ngram2kernel(ngram_c, args_c)
     out["C_kernel"], out["C_py"] = kernel_c, py_c
     run_case("C", kernel_c, py_c, args_c, B=5, L=11, seed=12, scale=1.5, ragged=True)
+
+    # ---- the steps either side of the path: CE_loss and frames_constrain_loss, reference source
+    # (utils/tools.py:538-557, 419-434) executed through the same shim in fp64; tf.cast keeps float64 there.
+    real_cast = sys.modules["tensorflow"].cast
+    sys.modules["tensorflow"].cast = lambda x, dtype: (torch.as_tensor(x).to(torch.float64) if dtype == torch.float32
+                                                       else torch.as_tensor(x).to(dtype))
+    sys.modules["tensorflow"].float32 = torch.float32
+    rng = np.random.default_rng(21)
+    B, T, V = 4, 13, 12
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    labels = rng.integers(0, V, size=(B, T)).astype(np.int32)
+    labels[0, 9:] = 0
+    labels[2, 5:] = 0
+    lg = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    ce = tools.CE_loss(lg, torch.tensor(labels), V, confidence=0.9)
+    ce.backward()
+    out["D_logits"], out["D_labels"] = logits, labels
+    out["D_loss_f64"], out["D_dlogits_f64"] = ce.detach().numpy(), lg.grad.numpy()
+    print("D CE_loss f64 %.15g" % float(ce))
+    align = np.zeros((B, 5), np.int32)
+    for b in range(B):
+        cuts = np.sort(rng.choice(np.arange(1, T - 1), size=int(rng.integers(2, 5)), replace=False))
+        align[b, :len(cuts)] = cuts
+    lg = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    fs = tools.frames_constrain_loss(lg, torch.tensor(align.copy()))
+    fs.backward()
+    out["E_align"] = align
+    out["E_loss_f64"], out["E_dlogits_f64"] = fs.detach().numpy(), lg.grad.numpy()
+    print("E frames_constrain_loss f64 %.15g" % float(fs))
+    sys.modules["tensorflow"].cast = real_cast
 
     np.savez_compressed(os.path.join(HERE, "eodm_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "eodm_golden.npz"))

@@ -343,3 +343,65 @@ def test_dense_bigram_agrees_with_table_path(eodm):
     sel = Cm[torch.tensor(ids[:, 0].astype(np.int64), device=dev), torch.tensor(ids[:, 1].astype(np.int64), device=dev)]
     assert float(((sel - counts[:3000]).abs() / counts[:3000]).max()) <= TOL
     assert float(N) == float(counts[3000])
+
+
+def test_ce_loss_vs_reference_source_and_oracle(eodm, golden):
+    """eodm_ce_loss vs the reference's CE_loss source run through the shim (golden D), and the oracle at size."""
+    dev = _dev()
+    lg = torch.tensor(golden["D_logits"], device=dev, requires_grad=True)
+    loss = eodm.CE_loss(lg, torch.tensor(golden["D_labels"], device=dev), 12, confidence=0.9)
+    loss.backward()
+    assert abs(float(loss) - float(golden["D_loss_f64"])) <= TOL * abs(float(golden["D_loss_f64"]))
+    assert rel_max(lg.grad.cpu().numpy(), golden["D_dlogits_f64"]) <= TOL
+    rng = np.random.default_rng(5)
+    B, T, V = 250, 180, 48                                  # the 250 paired utterances of BASELINE config 5
+    logits = (rng.standard_normal((B, T, V)) * 3).astype(np.float32)
+    labels = rng.integers(0, V, size=(B, T)).astype(np.int32)
+    labels[np.arange(T)[None, :] >= rng.integers(20, T + 1, size=B)[:, None]] = 0
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    loss = eodm.CE_loss(lg, torch.tensor(labels, device=dev), V)
+    loss.backward()
+    ref_l, ref_g = O.ce_loss(logits, labels, V, 0.9)
+    assert abs(float(loss) - ref_l) <= TOL * abs(ref_l)
+    assert rel_max(lg.grad.cpu().numpy(), ref_g) <= TOL
+
+
+def test_frames_constrain_loss_vs_reference_source_and_oracle(eodm, golden):
+    dev = _dev()
+    align = golden["E_align"].copy()
+    lg = torch.tensor(golden["D_logits"], device=dev, requires_grad=True)
+    loss = eodm.frames_constrain_loss(lg, torch.tensor(align, device=dev))
+    loss.backward()
+    assert abs(float(loss) - float(golden["E_loss_f64"])) <= TOL * abs(float(golden["E_loss_f64"]))
+    assert rel_max(lg.grad.cpu().numpy(), golden["E_dlogits_f64"]) <= TOL
+    rng = np.random.default_rng(6)
+    B, T, V, L = 40, 230, 40, 30
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    align = np.zeros((B, L), np.int32)
+    for b in range(B):
+        k = int(rng.integers(3, L + 1))
+        align[b, :k] = np.sort(rng.choice(np.arange(1, T - 1), size=k, replace=False))
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    loss = eodm.frames_constrain_loss(lg, torch.tensor(align, device=dev))
+    loss.backward()
+    ref_l, ref_g = O.frames_constrain_loss(logits, align)
+    assert abs(float(loss) - ref_l) <= TOL * abs(ref_l)
+    assert rel_max(lg.grad.cpu().numpy(), ref_g) <= TOL
+
+
+def test_gather_softmax_and_full_train_step_losses(eodm):
+    """gather_nd + softmax fused (pad slots gather frame 0 and their gradients add up there), and the EODM part of
+    train_step composed from the fused ops: counts on the gathered posteriors."""
+    dev = _dev()
+    rng = np.random.default_rng(8)
+    B, T, V, L = 6, 50, 40, 12
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    idx = np.sort(rng.integers(1, T, size=(B, L)), axis=1).astype(np.int32)
+    idx[np.arange(L)[None, :] >= rng.integers(3, L + 1, size=B)[:, None]] = 0          # padded slots -> frame 0
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    px = eodm.gather_softmax(lg, torch.tensor(idx, device=dev))
+    ref = O.gather_softmax(logits, idx)
+    assert rel_max(px.detach().cpu().numpy(), ref) <= TOL
+    w = rng.standard_normal(ref.shape).astype(np.float32)
+    (px * torch.tensor(w, device=dev)).sum().backward()
+    assert rel_max(lg.grad.cpu().numpy(), O.gather_softmax_vjp(logits, idx, w)) <= TOL

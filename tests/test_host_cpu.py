@@ -116,6 +116,18 @@ def test_oracle_dense_bigram_equals_table_of_all_bigrams():
     assert np.allclose(O.bigram_dense_bwd(px, mask, G), O.counts_bwd(px, mask, ids, 2, G.reshape(-1)), rtol=1e-12, atol=1e-300)
 
 
+def test_oracle_ce_and_frames_constrain_match_reference_source(golden):
+    """CE_loss / frames_constrain_loss restatements vs the reference's own source run through the shim (fp64)."""
+    loss, dl = O.ce_loss(golden["D_logits"], golden["D_labels"], 12, 0.9)
+    assert abs(loss - golden["D_loss_f64"]) <= 1e-12 * abs(golden["D_loss_f64"])
+    assert np.abs(dl - golden["D_dlogits_f64"]).max() <= 1e-12
+    align = golden["E_align"].copy()
+    loss, dl = O.frames_constrain_loss(golden["D_logits"], align)
+    assert np.array_equal(align, golden["E_align"])                # not mutated
+    assert abs(loss - golden["E_loss_f64"]) <= 1e-12 * abs(golden["E_loss_f64"])
+    assert np.abs(dl - golden["E_dlogits_f64"]).max() <= 1e-12 * np.abs(golden["E_dlogits_f64"]).max()
+
+
 # ---------------------------------------------------------------- product host logic
 def test_tools_match_oracle_and_golden(eodm, golden, tmp_path):
     # a small n-gram file in the reference's format, including the unigram parse quirk

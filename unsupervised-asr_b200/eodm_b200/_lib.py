@@ -53,6 +53,12 @@ SIGNATURES = {
     "eodm_loss_from_counts": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _p]),
     "eodm_softmax_fwd": (_i, [_p, C.c_int64, _i, _p, _p]),
     "eodm_softmax_bwd": (_i, [_p, _p, C.c_int64, _i, _p, _p]),
+    "eodm_gather_softmax_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "eodm_gather_softmax_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "eodm_ce_loss_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "eodm_ce_loss": (_i, [_p, _p, C.c_int64, _i, C.c_float, _p, _p, _p, _p]),
+    "eodm_frames_constrain_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "eodm_frames_constrain_loss": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "eodm_prob_fwd": (_i, [_p, _p, _i, _i, _p, _p]),
     "eodm_prob_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "eodm_bigram_workspace_bytes": (C.c_size_t, [_i, _i, _i]),

@@ -87,3 +87,109 @@ def ngram_ids(ngram, n):
     for i, (z, _) in enumerate(ngram):
         ids[i, :len(z)] = z
     return ids
+
+
+# ---------------------------------------------------------------------------
+# the steps either side of the EODM loss inside train_step, on the GPU (torch CUDA tensors in and out)
+# ---------------------------------------------------------------------------
+def _aux():
+    import ctypes as C
+
+    import torch
+
+    from ._lib import check, lib
+    return C, torch, check, lib
+
+
+def gather_softmax(logits, idx):
+    """px = softmax(tf.gather_nd(logits, indices)) of main_EODM.py:163 + models/EODM.py:15, differentiable.
+    logits f32[B,T,V] (CUDA), idx int[B,L] = the frame index per slot (indices[..., 1] of stamps2indices)."""
+    C, torch, check, lib = _aux()
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, lg):
+            lg = lg.contiguous().float()
+            B, T, V = lg.shape
+            ix = idx.to(lg.device, torch.int32).contiguous()
+            L = ix.shape[1]
+            px = torch.empty((B, L, V), dtype=torch.float32, device=lg.device)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(lib.eodm_gather_softmax_fwd(C.c_void_p(lg.data_ptr()), C.c_void_p(ix.data_ptr()), B, T, L, V,
+                                              C.c_void_p(px.data_ptr()), st))
+            ctx.save_for_backward(px, ix)
+            ctx.shape = (B, T, L, V)
+            return px
+
+        @staticmethod
+        def backward(ctx, dpx):
+            px, ix = ctx.saved_tensors
+            B, T, L, V = ctx.shape
+            dpx = dpx.contiguous().float()
+            dl = torch.empty((B, T, V), dtype=torch.float32, device=px.device)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(lib.eodm_gather_softmax_bwd(C.c_void_p(px.data_ptr()), C.c_void_p(dpx.data_ptr()),
+                                              C.c_void_p(ix.data_ptr()), B, T, L, V, C.c_void_p(dl.data_ptr()), st))
+            return dl
+
+    return Fn.apply(logits)
+
+
+def CE_loss(logits, labels, vocab_size, confidence=0.9):
+    """utils/tools.py:538-557, same signature; logits f32[B,T,V] (CUDA), labels int[B,T].  0-dim CUDA tensor."""
+    C, torch, check, lib = _aux()
+    if logits.shape[-1] != vocab_size:
+        from ._lib import ESHAPE, EodmError
+        raise EodmError(ESHAPE, "logits have %d classes, vocab_size=%d" % (logits.shape[-1], vocab_size))
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, lg):
+            lg = lg.contiguous().float()
+            lab = labels.to(lg.device, torch.int32).contiguous()
+            rows = lab.numel()
+            loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+            dl = torch.empty_like(lg)
+            ws = torch.empty(lib.eodm_ce_loss_workspace_bytes(rows), dtype=torch.uint8, device=lg.device)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(lib.eodm_ce_loss(C.c_void_p(lg.data_ptr()), C.c_void_p(lab.data_ptr()), rows, int(vocab_size),
+                                   C.c_float(confidence), C.c_void_p(loss.data_ptr()), C.c_void_p(dl.data_ptr()),
+                                   C.c_void_p(ws.data_ptr()), st))
+            ctx.save_for_backward(dl)
+            return loss.reshape(())
+
+        @staticmethod
+        def backward(ctx, g):
+            (dl,) = ctx.saved_tensors
+            return dl * g
+
+    return Fn.apply(logits)
+
+
+def frames_constrain_loss(logits, align):
+    """utils/tools.py:419-434, same signature; logits f32[B,T,V] (CUDA), align int[B,L] (segment end stamps,
+    0-padded).  Unlike the reference, `align` is left untouched (the reference does `align += 1` in place)."""
+    C, torch, check, lib = _aux()
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, lg):
+            lg = lg.contiguous().float()
+            B, T, V = lg.shape
+            al = torch.as_tensor(align).to(lg.device, torch.int32).contiguous()
+            loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+            dl = torch.empty_like(lg)
+            ws = torch.empty(lib.eodm_frames_constrain_workspace_bytes(B, T, V), dtype=torch.uint8, device=lg.device)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(lib.eodm_frames_constrain_loss(C.c_void_p(lg.data_ptr()), C.c_void_p(al.data_ptr()), B, T, al.shape[1],
+                                                 V, C.c_void_p(loss.data_ptr()), C.c_void_p(dl.data_ptr()),
+                                                 C.c_void_p(ws.data_ptr()), st))
+            ctx.save_for_backward(dl)
+            return loss.reshape(())
+
+        @staticmethod
+        def backward(ctx, g):
+            (dl,) = ctx.saved_tensors
+            return dl * g
+
+    return Fn.apply(logits)
