@@ -13,9 +13,11 @@
 // fp32-faithful through the 3xTF32 split (hi = 10 mantissa bits, lo = the exact remainder;
 // D += A_hi B_hi + A_lo B_hi + A_hi B_lo).  Both operands pass through the CUDA cores once (eps, mask,
 // split) and are written to shared memory in the canonical K-major no-swizzle layout, 4 stages.
-// The accumulator tile D[128 x 256] lives in TMEM for 16 K-steps, then is added (round to nearest) into an
-// fp32 tile in shared memory -- the tensor core accumulates with truncation and drifts by -3.7e-8 per MMA --
-// while the other TMEM bank takes the next 16 steps.  One output tile is owned by one CTA for the whole K
+// The raw fp32 operand items arrive through an 8-deep cp.async ring (each thread fetches and later consumes its
+// own items, so the ring needs no block-level synchronisation and hides the global-load latency).
+// The accumulator tile D[128 x 256] lives in TMEM for 16 K-steps, then is added (round to nearest) into
+// fp32 sums in registers -- the tensor core accumulates with truncation and drifts by -3.7e-8 per MMA --
+// while the other TMEM bank takes the next 16 steps.  MMAs are issued by thread 0, one step behind production.  One output tile is owned by one CTA for the whole K
 // loop: no partial sums, no atomics, bit-reproducible.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,12 +30,14 @@
 namespace {
 using namespace eodm_tc;
 
-constexpr int kProd = 512;             // producer / epilogue threads
-constexpr int kThreadsG = kProd + 32;  // + the MMA-issuing warp
-constexpr int kSt = 3;                 // operand stages
-constexpr int kRound = 16;             // K-steps per accumulation round
+constexpr int kThreadsG = 512;  // warpgroups 0-2 produce operands (each owns every third K-step); warp 12 issues MMAs
+constexpr int kProdWG = 3;
+constexpr int kSt = 6;          // operand stages (hi/lo, canonical K-major): two per producing warpgroup
+constexpr int kRound = 16;      // K-steps per accumulation round
 constexpr int kTM = 128, kTN = 256, kTK = 8;
 constexpr int kStageFloats = 2 * kTM * kTK + 2 * kTN * kTK;  // A_hi, A_lo, B_hi, B_lo
+constexpr int kRawFloats = (kTM + kTN) * kTK;                // raw fp32 operands of one K-step
+constexpr int kRawSlots = 2 * kProdWG;                       // cp.async double buffer per warpgroup
 
 struct G3Args {
   const float* A;
@@ -54,65 +58,89 @@ struct G3Bars {
   uint64_t full[kSt], free_[kSt], d_full[2], d_empty[2];
 };
 
-struct Item {  // four consecutive k of one operand row
-  float x[4];
-};
-
-template <bool KCONTIG>
-__device__ __forceinline__ Item load_item(const float* __restrict__ P, long long ld_r, long long ld_k, int row,
-                                          int row_lim, int k0, int k_lim, float eps, const float* __restrict__ sk) {
-  Item it;
-  const bool rv = row < row_lim;
-  if (KCONTIG) {
-    if (rv && k0 + 3 < k_lim) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(P + row * ld_r + k0));
-      it.x[0] = v.x + eps; it.x[1] = v.y + eps; it.x[2] = v.z + eps; it.x[3] = v.w + eps;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) it.x[q] = (rv && k0 + q < k_lim) ? __ldg(P + row * ld_r + k0 + q) + eps : 0.f;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      it.x[q] = (rv && k0 + q < k_lim) ? __ldg(P + row * ld_r + (long long)(k0 + q) * ld_k) + eps : 0.f;
-  }
-  if (sk) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) it.x[q] *= (k0 + q < k_lim) ? __ldg(sk + k0 + q) : 0.f;
-  }
-  return it;
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // hi / lo halves of four k values of row `row` into a K-major operand of `rows` rows
-__device__ __forceinline__ void store_item(float* hi, float* lo, int rows, int row, int kh, const Item& it) {
+__device__ __forceinline__ void store_item(float* hi, float* lo, int rows, int row, int kh, const float4& x) {
   uint32_t h[4], l[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) split_tf32(it.x[q], h[q], l[q]);
+  split_tf32(x.x, h[0], l[0]);
+  split_tf32(x.y, h[1], l[1]);
+  split_tf32(x.z, h[2], l[2]);
+  split_tf32(x.w, h[3], l[3]);
   const int off = kh * rows * 4 + (row >> 3) * 32 + (row & 7) * 4;  // floats
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Pipeline.  Producing one K-step's operands is a long dependent chain per thread (fetch -> wait -> read ->
+// eps/mask -> split -> store -> proxy fence -> barrier), about 3000 clk, while its three MMAs take 456 clk.  With
+// all warps cooperating on every step the kernel ran one step per chain latency; instead each of three
+// warpgroups owns every third K-step outright (six 16-byte items per thread, so the chain has instruction-level
+// parallelism) and the three chains overlap.  Warp 12 issues the MMAs in step order; all 16 warps drain the
+// accumulator rounds into registers.
+//
+// Operand fetch.  A K-contiguous operand (a row is contiguous along k) is fetched as 16-byte items of four k of
+// one row, raw layout [k half][row][4]; an MN-contiguous operand (for one k the rows are contiguous) as 16-byte
+// chunks of four rows of one k, raw layout [k][rows].  Items and chunks are spread over the warpgroup, so a
+// named barrier per warpgroup orders the landing of a raw buffer before its reads, and the reads before its refill.
+template <bool KC, int ROWS>
+struct Operand {
+  // issue this thread's share of the operand's chunks for K-step ks of the tile starting at row0
+  __device__ __forceinline__ static void fetch(float* dst, const float* __restrict__ P, long long ld_r, long long ld_k,
+                                               int row0, int row_lim, int ks, int k_lim, int l128) {
+#pragma unroll
+    for (int j = 0; j < (2 * ROWS) / 128; ++j) {
+      const int c = l128 + 128 * j;
+      if (KC) {
+        const int row = row0 + (c % ROWS), k = ks * kTK + (c / ROWS) * 4;
+        const bool v = row < row_lim && k + 3 < k_lim;
+        cp_async16(dst + c * 4, P + (v ? (long long)row * ld_r + k : 0), v);
+      } else {
+        const int r4 = (c % (ROWS / 4)) * 4, k = ks * kTK + c / (ROWS / 4);
+        const bool v = row0 + r4 + 3 < row_lim && k < k_lim;
+        cp_async16(dst + (c / (ROWS / 4)) * ROWS + r4, P + (v ? (long long)(row0 + r4) + (long long)k * ld_k : 0), v);
+      }
+    }
+  }
+  // four k (k half kh) of row `row` from the raw buffer
+  __device__ __forceinline__ static float4 read(const float* src, int row, int kh) {
+    if (KC) return *reinterpret_cast<const float4*>(src + (kh * ROWS + row) * 4);
+    const float* p = src + (kh * 4) * ROWS + row;
+    return make_float4(p[0], p[ROWS], p[2 * ROWS], p[3 * ROWS]);
+  }
+};
+
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_constant__ G3Args a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  float* stages = reinterpret_cast<float*>(smem_raw);
-  float* acc_s = stages + (size_t)kSt * kStageFloats;  // [kTN][kTM]: the running fp32 sums of this CTA's tile
+  float* stages = reinterpret_cast<float*>(smem_raw);        // [kSt][kStageFloats]
+  float* raw = stages + (size_t)kSt * kStageFloats;          // [kRawSlots][A: 128 x 8 | B: 256 x 8]
   __shared__ __align__(8) G3Bars bars;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tasks = a.m_tiles * a.n_tiles;
   const int ksteps = (a.K + kTK - 1) / kTK;
+  const int my_tasks = (n_tasks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tasks of this CTA
+  const int total_steps = my_tasks * ksteps;
+  const int rounds_per_task = (ksteps + kRound - 1) / kRound;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < kSt; ++s) {
-      mbar_init(&bars.full[s], kProd / 32);
+      mbar_init(&bars.full[s], 4);  // the four warps of the producing warpgroup
       mbar_init(&bars.free_[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.d_full[s], 1);
-      mbar_init(&bars.d_empty[s], kProd / 32);
+      mbar_init(&bars.d_empty[s], kThreadsG / 32);
     }
     fence_mbar_init();
   }
@@ -121,83 +149,32 @@ __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == kProd / 32) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((kTM >> 4) << 24);
-      int g = 0, rcount = 0;
-      for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        for (int ks = 0; ks < ksteps; ++ks, ++g) {
-          const int s = g % kSt, use = g / kSt;
-          const bool first = (ks % kRound) == 0;
-          if (first) {
-            ++rcount;
-            const int r = rcount - 1;
-            if (r >= 2) mbar_wait(&bars.d_empty[r & 1], (uint32_t)(((r >> 1) - 1) & 1));
-          }
-          const int bank = (rcount - 1) & 1;
-          mbar_wait(&bars.full[s], (uint32_t)(use & 1));
-          tc_fence_after();
-          const uint32_t base = smem_u32(stages + (size_t)s * kStageFloats);
-          const uint64_t ahi = smem_desc_kmajor(base, kTM * 16u, 128u);
-          const uint64_t alo = smem_desc_kmajor(base + kTM * kTK * 4u, kTM * 16u, 128u);
-          const uint64_t bhi = smem_desc_kmajor(base + 2u * kTM * kTK * 4u, kTN * 16u, 128u);
-          const uint64_t blo = smem_desc_kmajor(base + 2u * kTM * kTK * 4u + kTN * kTK * 4u, kTN * 16u, 128u);
-          const uint32_t d = tmem + (uint32_t)(bank * kTN);
-          mma_tf32_ss(d, ahi, bhi, idesc, first ? 0u : 1u);
-          mma_tf32_ss(d, alo, bhi, idesc, 1u);
-          mma_tf32_ss(d, ahi, blo, idesc, 1u);
-          mma_commit(&bars.free_[s]);
-          if ((ks % kRound) == kRound - 1 || ks == ksteps - 1) mma_commit(&bars.d_full[bank]);
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ producers + epilogue
-    const int wg = warp >> 2, quarter = warp & 3;
-    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    const int rowA = tid & (kTM - 1), khA = tid >> 7;  // threads 0..255 carry an A item
-    const int rowB = tid & (kTN - 1), khB = tid >> 8;  // every thread carries a B item
-    const bool hasA = tid < 2 * kTM;
-    float* acc = acc_s + (size_t)(wg * 64) * kTM + quarter * 32 + lane;  // this thread's 64 columns, stride kTM
-    bool fresh = true;  // the next drain starts a new output tile: store instead of add
+  const int wg = warp >> 2, quarter = warp & 3, l128 = tid & 127;
+  const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+  float acc[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) acc[k] = 0.f;
 
-    struct Pos {
-      int task, ks;
-    };
-    auto advance = [&](Pos p) {
-      if (++p.ks == ksteps) {
-        p.ks = 0;
-        p.task += gridDim.x;
-      }
-      return p;
-    };
-    auto load = [&](Pos p, Item& ia, Item& ib) {
-      if (p.task >= n_tasks) return;
-      const int m0 = (p.task % a.m_tiles) * kTM, n0 = (p.task / a.m_tiles) * kTN;
-      const int k0 = p.ks * kTK;
-      if (hasA) ia = load_item<A_KC>(a.A, a.lda_m, a.lda_k, m0 + rowA, a.Ma, k0 + khA * 4, a.Ka, a.eps_a, a.scale_k);
-      ib = load_item<B_KC>(a.B, a.ldb_n, a.ldb_k, n0 + rowB, a.Nb, k0 + khB * 4, a.Kb, a.eps_b, nullptr);
-    };
-    auto drain = [&](int r) {
-      const int bank = r & 1;
-      mbar_wait(&bars.d_full[bank], (uint32_t)((r >> 1) & 1));
-      tc_fence_after();
+  // ---- accumulator rounds: every warp drains every round (64 columns of its 32 lanes), in round order
+  int drained = 0;  // rounds this warp has drained so far
+  auto drain_next = [&]() {
+    const int r = drained++;
+    const int bank = r & 1;
+    mbar_wait(&bars.d_full[bank], (uint32_t)((r >> 1) & 1));
+    tc_fence_after();
 #pragma unroll
-      for (int cg = 0; cg < 64; cg += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + lane_field + (uint32_t)(bank * kTN + wg * 64 + cg), v);
-        tmem_wait_ld();
+    for (int cg = 0; cg < 64; cg += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + lane_field + (uint32_t)(bank * kTN + wg * 64 + cg), v);
+      tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          acc[(cg + k) * kTM] = (fresh ? 0.f : acc[(cg + k) * kTM]) + __uint_as_float(v[k]);
-      }
-      fresh = false;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.d_empty[bank]);
-    };
-    auto write_out = [&](int task) {
+      for (int k = 0; k < 16; ++k) acc[cg + k] += __uint_as_float(v[k]);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars.d_empty[bank]);
+    if ((r + 1) % rounds_per_task == 0) {  // the task's last round: its tile is complete
+      const int task = blockIdx.x + (r / rounds_per_task) * gridDim.x;
       const int m0 = (task % a.m_tiles) * kTM, n0 = (task / a.m_tiles) * kTN;
       const int i = m0 + quarter * 32 + lane;
       if (i < a.M) {
@@ -205,10 +182,9 @@ __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_
         float* out = a.C + (i + a.c_row_shift) * a.ldc + n0 + wg * 64;
         const int jn = a.N - (n0 + wg * 64);
         if (jn >= 64 && (((uintptr_t)out) & 15) == 0) {
-#pragma unroll 4
+#pragma unroll
           for (int k = 0; k < 64; k += 4) {
-            float4 v = make_float4(acc[k * kTM] * so, acc[(k + 1) * kTM] * so, acc[(k + 2) * kTM] * so,
-                                   acc[(k + 3) * kTM] * so);
+            float4 v = make_float4(acc[k] * so, acc[k + 1] * so, acc[k + 2] * so, acc[k + 3] * so);
             float4* o = reinterpret_cast<float4*>(out + k);
             if (a.accumulate) {
               const float4 c = *o;
@@ -217,49 +193,135 @@ __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_
             *o = v;
           }
         } else {
+#pragma unroll
           for (int k = 0; k < 64; ++k)
-            if (k < jn) out[k] = (a.accumulate ? out[k] : 0.f) + acc[k * kTM] * so;
+            if (k < jn) out[k] = (a.accumulate ? out[k] : 0.f) + acc[k] * so;
         }
       }
-      fresh = true;
-    };
-
-    Pos p1{(int)blockIdx.x, 0};
-    Pos p2 = advance(p1);
-    Item a1, b1, a2, b2;
-    load(p1, a1, b1);
-    load(p2, a2, b2);
-    int g = 0, rcount = 0, prev_task = -1;
-    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-#pragma unroll 1
-      for (int ks = 0; ks < ksteps; ++ks, ++g) {
-        const int s = g % kSt, use = g / kSt;
-        if (use > 0) mbar_wait(&bars.free_[s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage are done
-        float* st = stages + (size_t)s * kStageFloats;
-        if (hasA) store_item(st, st + kTM * kTK, kTM, rowA, khA, a1);
-        store_item(st + 2 * kTM * kTK, st + 2 * kTM * kTK + kTN * kTK, kTN, rowB, khB, b1);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.full[s]);
-        a1 = a2;
-        b1 = b2;
-        p2 = advance(p2);
-        load(p2, a2, b2);
-        if ((ks % kRound) == 0) {
-          ++rcount;
-          if (rcount >= 2) {  // the round that ended just before this K-step
-            drain(rcount - 2);
-            if (ks == 0) write_out(prev_task);
-          }
-        }
-      }
-      prev_task = task;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) acc[k] = 0.f;
     }
-    if (rcount >= 1) {
-      drain(rcount - 1);
-      write_out(prev_task);
+  };
+  // rounds that are complete once global step g has been issued: all rounds before the one containing g
+  auto round_of_step = [&](int g) { return (g / ksteps) * rounds_per_task + (g % ksteps) / kRound; };
+  const int total_rounds = my_tasks * rounds_per_task;
+
+  if (wg < kProdWG) {
+    // ------------------------------------------------------------------ producers: steps g = wg, wg + 3, ...
+    float* rawbuf = raw + (size_t)(wg * 2) * kRawFloats;
+    const int bar_id = 1 + wg;
+    auto fetch_step = [&](int g, int buf) {
+      if (g < total_steps) {
+        const int task = blockIdx.x + (g / ksteps) * gridDim.x, ks = g % ksteps;
+        const int m0 = (task % a.m_tiles) * kTM, n0 = (task / a.m_tiles) * kTN;
+        float* dst = rawbuf + (size_t)buf * kRawFloats;
+        Operand<A_KC, kTM>::fetch(dst, a.A, a.lda_m, a.lda_k, m0, a.Ma, ks, a.Ka, l128);
+        Operand<B_KC, kTN>::fetch(dst + kTM * kTK, a.B, a.ldb_n, a.ldb_k, n0, a.Nb, ks, a.Kb, l128);
+      }
+      cp_async_commit();
+    };
+    fetch_step(wg, 0);
+    int it = 0;
+#pragma unroll 1
+    for (int g = wg; g < total_steps; g += kProdWG, ++it) {
+      const int buf = it & 1;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the other buffer's readers (previous step) are done
+      fetch_step(g + kProdWG, buf ^ 1);
+      cp_async_wait<1>();                                          // this thread's chunks of step g have landed ...
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // ... and the whole warpgroup's
+      const int task = blockIdx.x + (g / ksteps) * gridDim.x, ks = g % ksteps;
+      const int m0 = (task % a.m_tiles) * kTM, n0 = (task / a.m_tiles) * kTN;
+      const float* rs = rawbuf + (size_t)buf * kRawFloats;
+      const bool tail_a = (ks + 1) * kTK > a.Ka, tail_b = (ks + 1) * kTK > a.Kb;
+      float4 xa[2], xb[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = l128 + 128 * j, row = c & (kTM - 1), kh = c >> 7;
+        float4 x = Operand<A_KC, kTM>::read(rs, row, kh);
+        const bool rv = m0 + row < a.Ma;
+        const int k = ks * kTK + kh * 4;
+        float4 sk = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (a.scale_k && !tail_a) sk = __ldg(reinterpret_cast<const float4*>(a.scale_k + k));
+        if (tail_a) {
+          sk.x = k + 0 < a.Ka ? (a.scale_k ? __ldg(a.scale_k + k + 0) : 1.f) : 0.f;
+          sk.y = k + 1 < a.Ka ? (a.scale_k ? __ldg(a.scale_k + k + 1) : 1.f) : 0.f;
+          sk.z = k + 2 < a.Ka ? (a.scale_k ? __ldg(a.scale_k + k + 2) : 1.f) : 0.f;
+          sk.w = k + 3 < a.Ka ? (a.scale_k ? __ldg(a.scale_k + k + 3) : 1.f) : 0.f;
+          if (k + 0 >= a.Ka) x.x = 0.f;   // zero-filled by the copy, but eps must not be added
+          if (k + 1 >= a.Ka) x.y = 0.f;
+          if (k + 2 >= a.Ka) x.z = 0.f;
+          if (k + 3 >= a.Ka) x.w = 0.f;
+        }
+        xa[j].x = rv ? (x.x + a.eps_a) * sk.x : 0.f;
+        xa[j].y = rv ? (x.y + a.eps_a) * sk.y : 0.f;
+        xa[j].z = rv ? (x.z + a.eps_a) * sk.z : 0.f;
+        xa[j].w = rv ? (x.w + a.eps_a) * sk.w : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = l128 + 128 * j, row = c & (kTN - 1), kh = c >> 8;
+        const float4 x = Operand<B_KC, kTN>::read(rs + kTM * kTK, row, kh);
+        const bool rv = n0 + row < a.Nb;
+        const int k = ks * kTK + kh * 4;
+        xb[j].x = (rv && (!tail_b || k + 0 < a.Kb)) ? x.x + a.eps_b : 0.f;
+        xb[j].y = (rv && (!tail_b || k + 1 < a.Kb)) ? x.y + a.eps_b : 0.f;
+        xb[j].z = (rv && (!tail_b || k + 2 < a.Kb)) ? x.z + a.eps_b : 0.f;
+        xb[j].w = (rv && (!tail_b || k + 3 < a.Kb)) ? x.w + a.eps_b : 0.f;
+      }
+      const int s = g % kSt, use = g / kSt;
+      if (use > 0) mbar_wait(&bars.free_[s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage are done
+      float* st = stages + (size_t)s * kStageFloats;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = l128 + 128 * j;
+        store_item(st, st + kTM * kTK, kTM, c & (kTM - 1), c >> 7, xa[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = l128 + 128 * j;
+        store_item(st + 2 * kTM * kTK, st + 2 * kTM * kTK + kTN * kTK, kTN, c & (kTN - 1), c >> 8, xb[j]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.full[s]);
+      // rounds that ended before this step (their MMAs were issued by warp 12 in step order)
+      while (drained < round_of_step(g)) drain_next();
+    }
+    cp_async_wait<0>();
+  } else if (warp == 4 * kProdWG) {
+    // ------------------------------------------------------------------ MMA issuer (lane 0), then drains with its warp
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((kTM >> 4) << 24);
+#pragma unroll 1
+    for (int g = 0; g < total_steps; ++g) {
+      const int ks = g % ksteps, r = round_of_step(g), bank = r & 1;
+      const bool first = (ks % kRound) == 0;
+      if (first) {
+        // the previous round is fully issued: drain the one before it (its MMAs are long done), keeping one round of slack
+        while (drained < r - 1) drain_next();
+        if (lane == 0 && r >= 2) mbar_wait(&bars.d_empty[bank], (uint32_t)(((r >> 1) - 1) & 1));
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const int s = g % kSt, use = g / kSt;
+        mbar_wait(&bars.full[s], (uint32_t)(use & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(stages + (size_t)s * kStageFloats);
+        const uint64_t ahi = smem_desc_kmajor(base, kTM * 16u, 128u);
+        const uint64_t alo = smem_desc_kmajor(base + kTM * kTK * 4u, kTM * 16u, 128u);
+        const uint64_t bhi = smem_desc_kmajor(base + 2u * kTM * kTK * 4u, kTN * 16u, 128u);
+        const uint64_t blo = smem_desc_kmajor(base + 2u * kTM * kTK * 4u + kTN * kTK * 4u, kTN * 16u, 128u);
+        const uint32_t d = tmem + (uint32_t)(bank * kTN);
+        mma_tf32_ss(d, ahi, bhi, idesc, first ? 0u : 1u);
+        mma_tf32_ss(d, alo, bhi, idesc, 1u);
+        mma_tf32_ss(d, ahi, blo, idesc, 1u);
+        mma_commit(&bars.free_[s]);
+        if ((ks % kRound) == kRound - 1 || ks == ksteps - 1) mma_commit(&bars.d_full[bank]);
+      }
+      __syncwarp();
     }
   }
+  // every warp: the rounds it has not drained yet (warps 13-15 drain everything here)
+  while (drained < total_rounds) drain_next();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -281,7 +343,7 @@ __global__ void eodm_bigram_n_kernel(const int* __restrict__ cnt, float* __restr
 
 template <bool A_KC, bool B_KC>
 int launch_g3(const G3Args& a, int sm_count, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)kSt * kStageFloats + (size_t)kTM * kTN) + 128;
+  const size_t smem = sizeof(float) * ((size_t)kSt * kStageFloats + (size_t)kRawSlots * kRawFloats) + 128;
   auto k = eodm_gemm3x_kernel<A_KC, B_KC>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
