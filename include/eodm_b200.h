@@ -136,6 +136,11 @@ int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B, int T, in
 int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B, int T, int V, const float* G, float* dpx,
                           void* ws, void* stream);
 
+/* The prior's K bigrams inside the dense matrices, for a kernel_size-2 table: S[z] = C[ids[z]] (gather, then
+ * eodm_allreduce_counts moves K+1 floats instead of V*V) and G = scatter(gS) (duplicated table entries add up). */
+int eodm_bigram_gather(const eodm_table* t, const float* C, float* S, void* stream);
+int eodm_bigram_scatter(const eodm_table* t, const float* gS, float* G, void* stream);
+
 /* ---- batch sharding over the GPUs of one node (one process per GPU) ---- */
 /* In-place sum over ranks of the packed [S (K floats), N (1 float)] on `stream`
  * (ncclAllReduce over NVLink).  `comm` is an ncclComm_t.  NCCL is resolved with

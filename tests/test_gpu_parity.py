@@ -405,3 +405,24 @@ def test_gather_softmax_and_full_train_step_losses(eodm):
     w = rng.standard_normal(ref.shape).astype(np.float32)
     (px * torch.tensor(w, device=dev)).sum().backward()
     assert rel_max(lg.grad.cpu().numpy(), O.gather_softmax_vjp(logits, idx, w)) <= TOL
+
+
+def test_dense_bigram_loss_equals_table_loss(eodm):
+    """EODM_loss through the dense tcgen05 contraction (gather K entries, loss, scatter, two GEMMs) == EODM_loss
+    through the table walk == the oracle, for a bigram table with a duplicated entry."""
+    dev = _dev()
+    V, B, T, K = 256, 4, 40, 5000
+    ids, py = eodm.synth.table(V, 2, K, seed=12, min_id=0)
+    ids[K - 1] = ids[3]                                     # a duplicated bigram: its gradient adds up in G
+    logits, mask = O.synth_batch(B, T, V, seed=12, len_lo=5, scale=3.0)
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, V, device=0))
+    out = []
+    for fn in (eodm.EODM_loss_dense_bigram, eodm.EODM_loss):
+        lg = torch.tensor(logits, device=dev, requires_grad=True)
+        loss = fn(lg, torch.tensor(mask, device=dev), conv_op, K, py)
+        loss.backward()
+        out.append((float(loss), lg.grad.cpu().numpy()))
+    r = O.eodm_loss_direct(logits, mask, ids, 2, py)
+    for loss, grad in out:
+        assert abs(loss - r["loss"]) <= TOL * abs(r["loss"])
+        assert rel_max(grad, r["dlogits"]) <= TOL and rel_l2(grad, r["dlogits"]) <= TOL

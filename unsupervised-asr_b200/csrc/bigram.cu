@@ -341,6 +341,26 @@ __global__ void __launch_bounds__(256) eodm_bigram_prep_kernel(const uint8_t* __
 }
 __global__ void eodm_bigram_n_kernel(const int* __restrict__ cnt, float* __restrict__ N) { N[0] = (float)cnt[0]; }
 
+// S[z] = C[ids[z][0]][ids[z][1]] -- the K prior entries of the dense count matrix
+__global__ void __launch_bounds__(256) eodm_bigram_gather_kernel(const float* __restrict__ C, const int32_t* __restrict__ ids,
+                                                                 int K, int V, float* __restrict__ S) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z < K) S[z] = C[(size_t)ids[2 * z] * V + ids[2 * z + 1]];
+}
+// G[u][v] = sum of gS over the table entries that are the bigram (u, v) (G zeroed beforehand); the head of each
+// chain of duplicates adds the chain in table order: deterministic, no atomics
+__global__ void __launch_bounds__(256) eodm_bigram_scatter_kernel(const float* __restrict__ gS, const int32_t* __restrict__ ids,
+                                                                  const int32_t* __restrict__ next_dup,
+                                                                  const int32_t* __restrict__ is_first, int K, int V,
+                                                                  float* __restrict__ G) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z < K && is_first[z]) {
+    float s = 0.f;
+    for (int q = z; q >= 0; q = next_dup[q]) s += gS[q];
+    G[(size_t)ids[2 * z] * V + ids[2 * z + 1]] = s;
+  }
+}
+
 template <bool A_KC, bool B_KC>
 int launch_g3(const G3Args& a, int sm_count, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)kSt * kStageFloats + (size_t)kRawSlots * kRawFloats) + 128;
@@ -476,4 +496,45 @@ extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B
   a.c_row_shift = 1; a.accumulate = 1;
   a.m_tiles = (int)((NR - 1 + kTM - 1) / kTM);
   return launch_g3<true, false>(a, sms, st);
+}
+
+// The table entries inside the dense matrices: S = gather(C), G = scatter(gS) (models/EODM.py:19-23 see only the
+// K n-grams of the prior, whatever else the dense contraction produced).
+extern "C" int eodm_bigram_gather(const eodm_table* t, const float* C, float* S, void* stream) {
+  if (!t || !C || !S) {
+    eodm_set_error("null pointer");
+    return EODM_EINVAL;
+  }
+  if (t->n != 2 || !t->full_order || t->device < 0) {
+    eodm_set_error("dense bigram path needs a device table of kernel_size 2 whose n-grams are all bigrams");
+    return EODM_EUNSUPPORTED;
+  }
+  eodm_bigram_gather_kernel<<<(t->K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(C, t->d_ids, t->K, t->V, S);
+  if (cudaGetLastError() != cudaSuccess) {
+    eodm_set_error("eodm_bigram_gather_kernel launch failed");
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
+
+extern "C" int eodm_bigram_scatter(const eodm_table* t, const float* gS, float* G, void* stream) {
+  if (!t || !gS || !G) {
+    eodm_set_error("null pointer");
+    return EODM_EINVAL;
+  }
+  if (t->n != 2 || !t->full_order || t->device < 0) {
+    eodm_set_error("dense bigram path needs a device table of kernel_size 2 whose n-grams are all bigrams");
+    return EODM_EUNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(G, 0, sizeof(float) * (size_t)t->V * t->V, st) != cudaSuccess) {
+    eodm_set_error("cudaMemsetAsync failed");
+    return EODM_ECUDA;
+  }
+  eodm_bigram_scatter_kernel<<<(t->K + 255) / 256, 256, 0, st>>>(gS, t->d_ids, t->d_next_dup, t->d_is_first, t->K, t->V, G);
+  if (cudaGetLastError() != cudaSuccess) {
+    eodm_set_error("eodm_bigram_scatter_kernel launch failed");
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
 }

@@ -357,8 +357,32 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
     rc = upload(t, order0, &d);
     t->d_order0 = (int32_t*)d;
   }
+  t->d_next_dup = nullptr;
+  t->d_is_first = nullptr;
   t->full_order = n >= 2;
   for (int z = 0; z < K; ++z) t->full_order = t->full_order && t->order[z] == n;
+  if (rc == EODM_OK && !host_only && n == 2 && t->full_order) {
+    // chains of identical bigrams, in table order
+    std::vector<int32_t> idx(K), next_dup(K, -1), is_first(K, 1);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
+      if (ids[(size_t)a * 2] != ids[(size_t)b * 2]) return ids[(size_t)a * 2] < ids[(size_t)b * 2];
+      return ids[(size_t)a * 2 + 1] < ids[(size_t)b * 2 + 1];
+    });
+    for (int i = 1; i < K; ++i)
+      if (ids[(size_t)idx[i] * 2] == ids[(size_t)idx[i - 1] * 2] &&
+          ids[(size_t)idx[i] * 2 + 1] == ids[(size_t)idx[i - 1] * 2 + 1]) {
+        next_dup[idx[i - 1]] = idx[i];
+        is_first[idx[i]] = 0;
+      }
+    const int32_t* d = nullptr;
+    rc = upload(t, next_dup, &d);
+    t->d_next_dup = (int32_t*)d;
+    if (rc == EODM_OK) {
+      rc = upload(t, is_first, &d);
+      t->d_is_first = (int32_t*)d;
+    }
+  }
   for (int j = 0; j < EODM_MAX_N; ++j) t->rows[j] = EodmRows{0, nullptr, nullptr, nullptr};
   if (rc == EODM_OK && !host_only && t->full_order) {
     for (int j = 0; j < n && rc == EODM_OK; ++j) {

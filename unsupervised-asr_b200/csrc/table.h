@@ -98,6 +98,8 @@ struct eodm_table {
   uint32_t* d_nodes_all;
   int32_t* d_node_z;
   int32_t* d_perm_all;        // all tries' leaf -> z maps back to back (offsets: trie[j].leaf_offset)
+  int32_t* d_next_dup;        // [K] next n-gram with the same ids (-1: none): chains of duplicates, for the
+  int32_t* d_is_first;        //     dense-bigram scatter; d_is_first[z] = 1 if z heads its chain
   bool full_order;            // every n-gram has order == n
   EodmRows rows[EODM_MAX_N];
   int64_t node_offset[EODM_MAX_N];

@@ -343,3 +343,48 @@ def bigram_dense_bwd(px, mask, G):
     ws = torch.empty(max(lib.eodm_bigram_workspace_bytes(B, T, V), 256), dtype=torch.uint8, device=px.device)
     check(lib.eodm_bigram_dense_bwd(_ptr(px), _ptr(mask), B, T, V, _ptr(G), _ptr(dpx), _ptr(ws), _stream()))
     return dpx
+
+
+class _DenseBigramLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, mask, py, table, comm):
+        logits = _f32c(logits, "_logits")
+        px = softmax_fwd(logits)
+        Cm, N = bigram_dense_fwd(px, mask)                         # all V*V expected bigram counts (tcgen05)
+        counts = torch.empty(table.K + 1, dtype=torch.float32, device=px.device)
+        check(lib.eodm_bigram_gather(table._h, _ptr(Cm), _ptr(counts), _stream()))
+        counts[table.K:] = N
+        if comm is not None:
+            comm.allreduce_counts(counts, table.K)                 # K+1 floats, not V*V
+        loss, gS = loss_from_counts(counts, py, table.K, True)
+        ctx.table, ctx.mask = table, mask
+        ctx.save_for_backward(px, gS)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        px, gS = ctx.saved_tensors
+        V = ctx.table.V
+        G = torch.empty((V, V), dtype=torch.float32, device=px.device)
+        check(lib.eodm_bigram_scatter(ctx.table._h, _ptr(gS), _ptr(G), _stream()))
+        dpx = bigram_dense_bwd(px, ctx.mask, G)
+        return softmax_bwd(px, dpx) * gout, None, None, None, None
+
+
+def EODM_loss_dense_bigram(_logits, mask, conv_op, k, py):
+    """EODM_loss (models/EODM.py:5-25) for a kernel_size-2 table over a large vocabulary (V a multiple of 128):
+    the expected counts of ALL bigrams come from one tensor-core contraction, the K prior entries are gathered
+    from it.  Same arguments and result as EODM_loss."""
+    if not isinstance(conv_op, PNgram):
+        raise TypeError("conv_op must come from eodm_b200.P_Ngram")
+    table = conv_op.table
+    if table.n != 2:
+        raise EodmError(_lib.EUNSUPPORTED, "dense bigram path needs kernel_size 2, table has %d" % table.n)
+    if k != table.K:
+        raise EodmError(_lib.ESHAPE, "k=%d but the table holds %d n-grams" % (k, table.K))
+    if not isinstance(py, torch.Tensor):
+        py = torch.as_tensor(np.asarray(py, dtype=np.float32))
+    py = py.to(_logits.device, torch.float32).contiguous()
+    if py.numel() != table.K:
+        raise EodmError(_lib.ESHAPE, "len(py)=%d != K=%d" % (py.numel(), table.K))
+    return _DenseBigramLossFn.apply(_logits, _mask_u8(mask, _logits.device), py, table, conv_op.comm)

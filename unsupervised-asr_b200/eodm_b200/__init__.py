@@ -7,6 +7,6 @@ from ._lib import EodmError, LIB_PATH, lib  # noqa: F401
 from .tools import (load_vocab, read_ngram, ngram2kernel, ngram_ids, gather_softmax, CE_loss,  # noqa: F401
                     frames_constrain_loss)
 from .EODM import (P_Ngram, EODM_loss, PNgram, NgramTable, softmax_fwd, softmax_bwd, counts_fwd, counts_bwd,  # noqa: F401
-                   loss_from_counts, bigram_dense_fwd, bigram_dense_bwd)
+                   loss_from_counts, bigram_dense_fwd, bigram_dense_bwd, EODM_loss_dense_bigram)
 from .session import Session  # noqa: F401
 from . import dist, synth  # noqa: F401
