@@ -262,6 +262,19 @@ def test_session_host_buffers(eodm):
     assert sess.loss(logits, mask) == loss                     # forward only, same bits
     with pytest.raises(eodm.EodmError):
         sess.loss(np.zeros((9, 60, 40), np.float32), np.ones((9, 60), bool))   # larger than the session
+    # a batch large enough for the pipelined path (two halves over a copy stream), odd B
+    ids, py, logits, mask = _random_case(42, 40, 5, 1000, 65, 260, False, len_lo=20)
+    table = eodm.NgramTable.from_ids(ids, 40, device=0)
+    sess = eodm.Session(table, py, maxB=65, maxT=260)
+    dl = np.empty_like(logits)
+    loss = sess.loss(logits, mask, dl)
+    conv_op = eodm.PNgram(table)
+    lg = torch.tensor(logits, device="cuda:0", requires_grad=True)
+    ref = eodm.EODM_loss(lg, torch.tensor(mask, device="cuda:0"), conv_op, 1000, py)
+    ref.backward()
+    assert abs(loss - float(ref)) <= 1e-6 * abs(float(ref))
+    assert rel_max(dl, lg.grad.cpu().numpy().astype(np.float64)) <= 1e-6
+    assert sess.loss(logits, mask, dl) == loss
 
 
 def test_full_size_properties(eodm):

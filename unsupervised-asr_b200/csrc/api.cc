@@ -219,9 +219,11 @@ extern "C" int eodm_allreduce_counts(void* comm, float* S, int K, float* N, void
 struct eodm_session {
   const eodm_table* t;
   int maxB, maxT, device;
-  cudaStream_t st;
+  cudaStream_t st, copy_st;       // compute stream, copy stream of the pipelined host-buffer step
+  cudaEvent_t ev_in[2], ev_out[2], ev_done;
   float *logits, *px, *dpx, *dlogits;
-  float* counts;  // [K + 1]: S then N (packed for one all-reduce)
+  float* counts;   // [K + 1]: S then N (packed for one all-reduce)
+  float* counts2;  // [2][K + 1]: per-chunk partial counts of the pipelined step
   float *py, *gS, *loss;
   uint8_t* mask;
   void* ws;
@@ -232,9 +234,12 @@ static void session_free(eodm_session* s) {
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(s->device);
-  void* ptrs[] = {s->logits, s->px, s->dpx, s->dlogits, s->counts, s->py, s->gS, s->loss, s->mask, s->ws};
+  void* ptrs[] = {s->logits, s->px, s->dpx, s->dlogits, s->counts, s->counts2, s->py, s->gS, s->loss, s->mask, s->ws};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t ev : {s->ev_in[0], s->ev_in[1], s->ev_out[0], s->ev_out[1], s->ev_done})
+    if (ev) cudaEventDestroy(ev);
+  if (s->copy_st) cudaStreamDestroy(s->copy_st);
   if (s->st) cudaStreamDestroy(s->st);
   if (prev >= 0) cudaSetDevice(prev);
   delete s;
@@ -257,12 +262,19 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   const size_t rows = (size_t)maxB * maxT, el = rows * t->V * sizeof(float);
   cudaError_t e = cudaSetDevice(t->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->logits, el);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->px, el);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->dpx, el);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->dlogits, el);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->mask, rows);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts, ((size_t)t->K + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts2, 2 * ((size_t)t->K + 1) * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->py, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->gS, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
@@ -302,15 +314,81 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   return rc;
 }
 
+// Two halves of the batch, pipelined over a copy stream and the compute stream:
+//   H2D(0) H2D(1)                      |            D2H(0)      D2H(1)
+//          softmax+counts(0) softmax+counts(1) -> sum -> [allreduce] -> loss -> VJP(0) VJP(1)
+// Each half keeps a whole number of tiles per SM, so the kernels run as efficiently as on the full batch.
+static int session_loss_pipelined(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
+                                  void* comm, float* loss_host, float* dlogits_host) {
+  const eodm_table* t = s->t;
+  const int V = t->V, K = t->K;
+  const int Bc[2] = {B / 2, B - B / 2};
+  size_t row0[2] = {0, (size_t)Bc[0] * T};
+  int rc = EODM_OK;
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < 2 && e == cudaSuccess; ++c) {
+    const size_t rows = (size_t)Bc[c] * T;
+    e = cudaMemcpyAsync(s->logits + row0[c] * V, logits_host + row0[c] * V, rows * V * sizeof(float),
+                        cudaMemcpyHostToDevice, s->copy_st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(s->mask + row0[c], mask_host + row0[c], rows, cudaMemcpyHostToDevice, s->copy_st);
+    if (e == cudaSuccess) e = cudaEventRecord(s->ev_in[c], s->copy_st);
+  }
+  for (int c = 0; c < 2 && e == cudaSuccess && rc == EODM_OK; ++c) {
+    e = cudaStreamWaitEvent(s->st, s->ev_in[c], 0);
+    if (e != cudaSuccess) break;
+    float* cc = s->counts2 + (size_t)c * (K + 1);
+    rc = eodm_softmax_fwd_launch(s->logits + row0[c] * V, (int64_t)Bc[c] * T, V, s->px + row0[c] * V, s->st);
+    if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
+  }
+  if (e == cudaSuccess && rc == EODM_OK) rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  if (e == cudaSuccess && rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, s->counts, K, s->counts + K, s->st);
+  if (e == cudaSuccess && rc == EODM_OK)
+    rc = eodm_loss_launch(s->counts, s->counts + K, s->py, K, 1e-15f, s->loss, dlogits_host ? s->gS : nullptr, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(s->ev_done, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->copy_st, s->ev_done, 0);
+  if (e == cudaSuccess && rc == EODM_OK)
+    e = cudaMemcpyAsync(loss_host, s->loss, sizeof(float), cudaMemcpyDeviceToHost, s->copy_st);
+  for (int c = 0; c < 2 && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
+    const size_t rows = (size_t)Bc[c] * T;
+    rc = eodm_counts_bwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, s->gS, s->dpx + row0[c] * V, s->ws, s->st);
+    if (rc == EODM_OK)
+      rc = eodm_softmax_bwd_launch(s->px + row0[c] * V, s->dpx + row0[c] * V, (int64_t)rows, V, s->dlogits + row0[c] * V,
+                                   s->st);
+    if (rc != EODM_OK) break;
+    e = cudaEventRecord(s->ev_out[c], s->st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->copy_st, s->ev_out[c], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dlogits_host + row0[c] * V, s->dlogits + row0[c] * V, rows * V * sizeof(float),
+                          cudaMemcpyDeviceToHost, s->copy_st);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s->st);
+  cudaError_t e3 = cudaStreamSynchronize(s->copy_st);
+  if (rc != EODM_OK) return rc;
+  if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_session_loss: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
+
 extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
                                  void* comm, float* loss_host, float* dlogits_host) {
   REQUIRE(s && logits_host && mask_host && loss_host, EODM_EINVAL, "null pointer");
   REQUIRE(B >= 1 && B <= s->maxB && T >= 1 && T <= s->maxT, EODM_ESHAPE,
           "batch [%d,%d] exceeds the session's [%d,%d]", B, T, s->maxB, s->maxT);
+  REQUIRE(T >= s->t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, s->t->n);
   int prev = -1;
   cudaGetDevice(&prev);
   CUDA_TRY(cudaSetDevice(s->device));
   const size_t rows = (size_t)B * T, el = rows * s->t->V * sizeof(float);
+  // copies worth overlapping (>= 2 MiB each way) and two non-empty halves
+  if (B >= 2 && el >= ((size_t)2 << 20)) {
+    int rc = session_loss_pipelined(s, logits_host, mask_host, B, T, comm, loss_host, dlogits_host);
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+  }
   int rc = EODM_OK;
   cudaError_t e = cudaMemcpyAsync(s->logits, logits_host, el, cudaMemcpyHostToDevice, s->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->mask, mask_host, rows, cudaMemcpyHostToDevice, s->st);

@@ -183,6 +183,20 @@ __global__ void __launch_bounds__(256) eodm_prob_bwd_kernel(const float* __restr
     }                                                                             \
   } while (0)
 
+namespace {
+__global__ void __launch_bounds__(256) eodm_add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+}  // namespace
+
+int eodm_add_vectors_launch(const float* a, const float* b, int n, float* out, cudaStream_t st) {
+  eodm_add_vectors_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, n, out);
+  EODM_CHECK_LAUNCH("eodm_add_vectors_kernel");
+  return EODM_OK;
+}
+
 int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
                      cudaStream_t st) {
   eodm_loss_kernel<<<1, 1024, 0, st>>>(S, N, py, K, eps, loss, gS);
