@@ -32,12 +32,13 @@ using namespace eodm_tc;
 
 constexpr int kThreadsG = 512;  // warpgroups 0-2 produce operands (each owns every third K-step); warp 12 issues MMAs
 constexpr int kProdWG = 3;
-constexpr int kSt = 6;          // operand stages (hi/lo, canonical K-major): two per producing warpgroup
+constexpr int kSt = 3;          // operand stages (hi/lo, canonical K-major): one per producing warpgroup
+constexpr int kRawDepth = 3;    // cp.async buffers per warpgroup: operands are fetched two of its K-steps ahead
 constexpr int kRound = 16;      // K-steps per accumulation round
 constexpr int kTM = 128, kTN = 256, kTK = 8;
 constexpr int kStageFloats = 2 * kTM * kTK + 2 * kTN * kTK;  // A_hi, A_lo, B_hi, B_lo
 constexpr int kRawFloats = (kTM + kTN) * kTK;                // raw fp32 operands of one K-step
-constexpr int kRawSlots = 2 * kProdWG;                       // cp.async double buffer per warpgroup
+constexpr int kRawSlots = kRawDepth * kProdWG;               // cp.async ring per warpgroup
 
 struct G3Args {
   const float* A;
@@ -59,7 +60,7 @@ struct G3Bars {
 };
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
@@ -208,29 +209,51 @@ __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_
 
   if (wg < kProdWG) {
     // ------------------------------------------------------------------ producers: steps g = wg, wg + 3, ...
-    float* rawbuf = raw + (size_t)(wg * 2) * kRawFloats;
+    float* rawbuf = raw + (size_t)(wg * kRawDepth) * kRawFloats;
     const int bar_id = 1 + wg;
-    auto fetch_step = [&](int g, int buf) {
-      if (g < total_steps) {
-        const int task = blockIdx.x + (g / ksteps) * gridDim.x, ks = g % ksteps;
-        const int m0 = (task % a.m_tiles) * kTM, n0 = (task / a.m_tiles) * kTN;
+    // (task, K-step) cursors advance by kProdWG steps without divisions: one for the fetches, one for the consumption
+    struct Cursor {
+      int task, ks, m0, n0, tidx;  // tidx = how many of this CTA's tasks precede `task`
+    };
+    auto locate = [&](Cursor& c) {
+      c.m0 = (c.task % a.m_tiles) * kTM;
+      c.n0 = (c.task / a.m_tiles) * kTN;
+    };
+    auto advance = [&](Cursor& c) {
+      c.ks += kProdWG;
+      while (c.ks >= ksteps) {  // ksteps >= 1; kProdWG steps may cross more than one tiny task
+        c.ks -= ksteps;
+        c.task += gridDim.x;
+        ++c.tidx;
+        locate(c);
+      }
+    };
+    Cursor cf{(int)blockIdx.x, wg, 0, 0, 0}, cc{(int)blockIdx.x, wg, 0, 0, 0};
+    while (cf.ks >= ksteps) { cf.ks -= ksteps; cf.task += gridDim.x; ++cf.tidx; }
+    cc = cf;
+    locate(cf);
+    locate(cc);
+    auto fetch_step = [&](int buf) {
+      if (cf.task < n_tasks) {
         float* dst = rawbuf + (size_t)buf * kRawFloats;
-        Operand<A_KC, kTM>::fetch(dst, a.A, a.lda_m, a.lda_k, m0, a.Ma, ks, a.Ka, l128);
-        Operand<B_KC, kTN>::fetch(dst + kTM * kTK, a.B, a.ldb_n, a.ldb_k, n0, a.Nb, ks, a.Kb, l128);
+        Operand<A_KC, kTM>::fetch(dst, a.A, a.lda_m, a.lda_k, cf.m0, a.Ma, cf.ks, a.Ka, l128);
+        Operand<B_KC, kTN>::fetch(dst + kTM * kTK, a.B, a.ldb_n, a.ldb_k, cf.n0, a.Nb, cf.ks, a.Kb, l128);
+        advance(cf);
       }
       cp_async_commit();
     };
-    fetch_step(wg, 0);
+    for (int d = 0; d < kRawDepth - 1; ++d) fetch_step(d);
     int it = 0;
 #pragma unroll 1
     for (int g = wg; g < total_steps; g += kProdWG, ++it) {
-      const int buf = it & 1;
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the other buffer's readers (previous step) are done
-      fetch_step(g + kProdWG, buf ^ 1);
-      cp_async_wait<1>();                                          // this thread's chunks of step g have landed ...
+      const int buf = it % kRawDepth;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the buffer about to be refilled was read one step ago
+      fetch_step((it + kRawDepth - 1) % kRawDepth);
+      cp_async_wait<kRawDepth - 1>();                              // this thread's chunks of step g have landed ...
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // ... and the whole warpgroup's
-      const int task = blockIdx.x + (g / ksteps) * gridDim.x, ks = g % ksteps;
-      const int m0 = (task % a.m_tiles) * kTM, n0 = (task / a.m_tiles) * kTN;
+      const int ks = cc.ks, m0 = cc.m0, n0 = cc.n0;
+      const int round_here = cc.tidx * rounds_per_task + ks / kRound;
+      advance(cc);
       const float* rs = rawbuf + (size_t)buf * kRawFloats;
       const bool tail_a = (ks + 1) * kTK > a.Ka, tail_b = (ks + 1) * kTK > a.Kb;
       float4 xa[2], xb[4];
@@ -285,7 +308,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) eodm_gemm3x_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.full[s]);
       // rounds that ended before this step (their MMAs were issued by warp 12 in step order)
-      while (drained < round_of_step(g)) drain_next();
+      while (drained < round_here) drain_next();
     }
     cp_async_wait<0>();
   } else if (warp == 4 * kProdWG) {
