@@ -439,3 +439,38 @@ def test_dense_bigram_loss_equals_table_loss(eodm):
     for loss, grad in out:
         assert abs(loss - r["loss"]) <= TOL * abs(r["loss"])
         assert rel_max(grad, r["dlogits"]) <= TOL and rel_l2(grad, r["dlogits"]) <= TOL
+
+
+@pytest.mark.parametrize("V,n,K,B,T", [(64, 3, 60000, 3, 70),      # K too large for shared-memory accumulators
+                                       (800, 2, 5000, 2, 45),      # wide vocabulary: one window per lane (the walk's limit is V ~ 830)
+                                       (300, 3, 4000, 2, 50)])
+def test_resource_fallbacks_vs_oracle(eodm, V, n, K, B, T):
+    """Shapes that leave the default resource plan: global-memory accumulators, narrow tiles."""
+    ids, py = eodm.synth.table(V, n, K, seed=V)
+    logits, mask = O.synth_batch(B, T, V, seed=V, len_lo=n + 2)
+    loss, grad, _ = _loss_and_grad(eodm, ids, V, py, logits, mask, from_ids=True)
+    px64 = torch.softmax(torch.tensor(logits), -1).numpy().astype(np.float64)
+    S, N = O.counts_fwd(px64, mask, ids, n)
+    ref_loss, gS = O.loss_from_counts(S, N, py)
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss)
+    dpx = O.counts_bwd(px64, mask, ids, n, gS)
+    ref_grad = O.softmax_vjp(px64, dpx)
+    assert rel_max(grad, ref_grad) <= 2 * TOL      # fp32 softmax of the inputs is shared; the VJP is compared in fp64
+
+
+def test_unsupported_shape_is_reported(eodm):
+    ids, py = eodm.synth.table(6000, 2, 100, seed=1)
+    table = eodm.NgramTable.from_ids(ids, 6000, device=0)
+    px = torch.full((1, 8, 6000), 1.0 / 6000, device=_dev())
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.counts_fwd(table, px, torch.ones(1, 8, dtype=torch.bool, device=_dev()))
+    assert e.value.status == -5 and "shared memory" in str(e.value)
+    # V = 1000 still fits the forward tile but not the backward one (px tile + dpx tile): reported, not mis-computed
+    ids, py = eodm.synth.table(1000, 2, 100, seed=1)
+    table = eodm.NgramTable.from_ids(ids, 1000, device=0)
+    px = torch.full((1, 8, 1000), 1.0 / 1000, device=_dev())
+    m = torch.ones(1, 8, dtype=torch.bool, device=_dev())
+    eodm.counts_fwd(table, px, m)
+    with pytest.raises(eodm.EodmError) as e:
+        eodm.counts_bwd(table, px, m, torch.zeros(100, device=_dev()))
+    assert e.value.status == -5
