@@ -141,8 +141,15 @@ def import_reference():
     for name in ["editdistance", "nltk", "python_speech_features", "tqdm", "tensorflow_addons"]:
         if name not in sys.modules:
             m = types.ModuleType(name)
-            m.mfcc = m.logfbank = m.tqdm = None
+            m.mfcc = m.logfbank = None
+            m.tqdm = lambda x, *a, **k: x
             sys.modules[name] = m
+    # nltk is absent: the two symbols get_dataset_ngram / get_N_gram use, with nltk's documented behaviour
+    # (FreqDist is a collections.Counter subclass; ngrams() yields the consecutive n-tuples, no padding)
+    import collections
+    nl = sys.modules["nltk"]
+    nl.FreqDist = collections.Counter
+    nl.ngrams = lambda seq, n: (lambda t: (tuple(t[i:i + n]) for i in range(len(t) - n + 1)))(list(seq))
     sys.path.insert(0, REF)
     # utils/__init__ may not exist: import the two files as plain modules
     import importlib.util
@@ -276,6 +283,23 @@ def main():
     out["E_loss_f64"], out["E_dlogits_f64"] = fs.detach().numpy(), lg.grad.numpy()
     print("E frames_constrain_loss f64 %.15g" % float(fs))
     sys.modules["tensorflow"].cast = real_cast
+
+    # ---- f4: the n-gram file producer, reference source (utils/tools.py:219-252) on the shipped TIMIT transcripts
+    import tempfile
+    tools.tqdm = lambda x, *a, **k: x
+    src = open(os.path.join(REF, "data/timit/train_trans.txt")).readlines()[:400]
+    with tempfile.TemporaryDirectory() as td:
+        tf_in, tf_out = os.path.join(td, "trans.csv"), os.path.join(td, "out.3gram")
+        # the function wants `uttid,tokens,anything`
+        with open(tf_in, "w") as fw:
+            for ln in src:
+                uttid, seq = ln.strip().split(" ", 1)        # shipped file: `uttid tok tok ...`
+                fw.write("%s,%s,x\n" % (uttid, seq))
+        sys.modules["utils.dataProcess"].get_N_gram = dp.get_N_gram
+        tools.get_dataset_ngram(tf_in, 3, 50, savefile=tf_out, split=150)
+        out["F_trans_csv"] = np.array(open(tf_in).read())
+        out["F_ngram_file"] = np.array(open(tf_out).read())
+    print("F get_dataset_ngram: first lines", str(out["F_ngram_file"]).split("\n")[:2])
 
     np.savez_compressed(os.path.join(HERE, "eodm_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "eodm_golden.npz"))

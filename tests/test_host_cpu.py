@@ -158,6 +158,22 @@ def test_tools_match_oracle_and_golden(eodm, golden, tmp_path):
     assert np.array_equal(eodm.ngram_ids(ngram, 5), ids)
 
 
+def test_get_dataset_ngram_matches_reference_source(eodm, golden, tmp_path):
+    """f4: the n-gram file producer vs the reference's get_dataset_ngram run on 400 shipped TIMIT transcripts."""
+    src = tmp_path / "trans.csv"
+    src.write_text(str(golden["F_trans_csv"]))
+    out = tmp_path / "out.3gram"
+    counts = eodm.get_dataset_ngram(str(src), 3, 50, savefile=str(out), split=150)
+    assert out.read_text() == str(golden["F_ngram_file"])
+    assert counts.most_common(1)[0][1] >= 1
+    # and the file feeds read_ngram / ngram2kernel
+    t2i = {t: i for i, t in enumerate(sorted({tok for z in counts for tok in z}), 1)}
+    import collections
+    ngram, total = eodm.read_ngram(50, str(out), collections.defaultdict(int, t2i))
+    assert len(ngram) == 50 and abs(sum(p for _, p in ngram) - 1) < 1e-12
+    assert eodm.get_N_gram("a b a b a".split(), 2) == {("a", "b"): 2, ("b", "a"): 2}
+
+
 def test_table_round_trip_bit_exact(eodm, golden):
     for K in (1000, 10000):
         ids = golden["timit%d_ids" % K]

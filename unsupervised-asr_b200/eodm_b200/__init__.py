@@ -5,6 +5,7 @@ Importing this package loads libeodm_b200.so (built in-tree by
 """
 from ._lib import EodmError, LIB_PATH, lib  # noqa: F401
 from .tools import (load_vocab, read_ngram, ngram2kernel, ngram_ids, gather_softmax, CE_loss,  # noqa: F401
+                    get_N_gram, get_dataset_ngram,
                     frames_constrain_loss)
 from .EODM import (P_Ngram, EODM_loss, PNgram, NgramTable, softmax_fwd, softmax_bwd, counts_fwd, counts_bwd,  # noqa: F401
                    loss_from_counts, bigram_dense_fwd, bigram_dense_bwd, EODM_loss_dense_bigram)

@@ -193,3 +193,34 @@ def frames_constrain_loss(logits, align):
             return dl * g
 
     return Fn.apply(logits)
+
+
+# ---------------------------------------------------------------------------
+# n-gram table producers from transcripts (utils/tools.py:219-252, utils/dataProcess.py:180-192): host text work
+# ---------------------------------------------------------------------------
+def get_N_gram(iterator, n):
+    """Counter of the n-grams of one token sequence (no padding at the ends), like nltk's
+    FreqDist(ngrams(iterator, n)) in utils/dataProcess.py:180-192."""
+    tokens = list(iterator)
+    return collections.Counter(tuple(tokens[i:i + n]) for i in range(len(tokens) - n + 1))
+
+
+def get_dataset_ngram(text_file, n, k, savefile=None, split=5000):
+    """utils/tools.py:219-252.  `text_file` holds lines `uttid,token token ...,anything`; n-grams are counted per
+    utterance (no n-gram spans two utterances), summed over chunks of `split` utterances, and only the 2k most
+    common n-grams of each chunk enter the global count.  Writes the k most common as `('a', 'b'):count` lines --
+    the format read_ngram parses -- and returns the global Counter.  Ties keep first-seen order, as Counter does."""
+    with open(text_file) as f:
+        utterances = f.readlines()
+    ngrams_global = collections.Counter()
+    for i in range(len(utterances) // split + 1):
+        chunk = collections.Counter()
+        for utt in utterances[i * split:(i + 1) * split]:
+            _, seq_label, _ = utt.strip().split(',')
+            chunk += get_N_gram(seq_label.split(), n)
+        ngrams_global += dict(chunk.most_common(2 * k))
+    if savefile:
+        with open(savefile, 'w') as fw:
+            for ngram, num in ngrams_global.most_common(k):
+                fw.write('{}:{}\n'.format(ngram, num))
+    return ngrams_global
