@@ -112,7 +112,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -144,6 +144,23 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs next to its GPU, so that the pinned host buffers of the end-to-end leg are
+    allocated (first touch) on the GPU's own NUMA node and the copies of 8 ranks do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------
 def main():
     args = parse()
@@ -163,6 +180,7 @@ def main():
     assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     comm = None
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
@@ -227,7 +245,7 @@ def main():
         td.all_reduce(ft)
         frames_all = int(ft[0])
     value = frames_all / (ms_per_step * 1e-3)
-    clocks = sampler.summary(t0, t1) if rank == 0 else None
+    t_clk0 = t0
 
     # ---- the two counts kernels alone (rank-local; roofline of the dominant one) ----
     px = E.softmax_fwd(logits_d)
@@ -304,7 +322,10 @@ def main():
                "h2d_bytes_per_step": B * T * V * 4 + B * T, "d2h_bytes_per_step": B * T * V * 4 + 4,
                "loss": loss_val, "api": "eodm_session_loss (C ABI, pinned host buffers)"}
     if rank == 0:
+        clocks = sampler.summary(t_clk0, time.perf_counter())   # every timed region of this run
         sampler.stop()
+    else:
+        clocks = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -322,6 +343,7 @@ def main():
             "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
                        "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
+                       "host_cpus_per_rank": numa,
                        "path": "cuda-core trie walk (v2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),

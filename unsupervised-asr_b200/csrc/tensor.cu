@@ -11,18 +11,21 @@
 // the dense product is cheaper than the sparse one.
 //
 // Mapping.  The M dimension (128 TMEM lanes) is the prefix row, N is the last phone (V padded to 16),
-// K is the window index, 8 windows (one tf32 MMA K step) per chunk.  A CTA owns up to 6 M tiles whose
-// fp32 accumulators D[128 x Npad] stay resident in TMEM for the CTA's whole slice of the batch; CTAs
-// are arranged as (M-tile group) x (batch slice).  The A operand never touches shared memory: the
-// producer threads (thread = TMEM lane = prefix row) form Q for 8 windows in registers from a staged
-// px tile and write it to TMEM with tcgen05.st; the B operand (8 windows x Npad phones) is written to
-// shared memory in the canonical K-major no-swizzle layout.  fp32 accuracy comes from the 3xTF32
-// split: x = hi + lo with hi = x rounded to 10 mantissa bits toward zero, and
-//     D += A_hi B_hi + A_lo B_hi + A_hi B_lo            (the dropped lo*lo term is 2^-22 relative).
-// MMAs are issued by one thread and complete asynchronously (tcgen05.commit -> mbarrier) while all
-// warps produce the next chunk into the other TMEM/shared stage.  At the end every CTA writes its
-// accumulators to a per-slice partial, and a second kernel gathers the K table entries and adds the
-// slices in a fixed order: deterministic, no float atomics.
+// K is the window index, 8 windows (one tf32 MMA K step) per chunk.  A CTA owns up to 3 M tiles (one per
+// producer warpgroup) and a slice of the batch; CTAs are arranged as (M-tile group) x (batch slice).  The A
+// operand never touches shared memory: the producer threads (thread = TMEM lane = prefix row) form Q for 8
+// windows in registers from a staged px tile and write it to TMEM with tcgen05.st; the B operand (8 windows x
+// Npad phones) is written to shared memory in the canonical K-major no-swizzle layout by a fourth warpgroup,
+// which also stages the next px tile.  fp32 accuracy comes from the 3xTF32 split (x = hi + lo, hi = the top 10
+// mantissa bits):  D += A_hi B_hi + A_lo B_hi + A_hi B_lo  (the dropped lo*lo term is 2^-22 relative).
+// MMAs are issued by one thread of a 17th warp and complete asynchronously (tcgen05.commit -> mbarrier), 4
+// operand stages deep.  At the end every CTA writes its sums to a per-slice partial, and a second kernel
+// gathers the K table entries and adds the slices in a fixed order: deterministic, no float atomics.
+//
+// STATUS: correct (3e-6 against the fp64 oracle) but NOT the default path.  One tf32 MMA costs 152 clk whatever
+// its N (tools/ubench_mma.cu), so with N = V = 48 the tensor core runs at a fifth of its rate and timit_c2
+// forward takes 540 us here against 250 us for the walk of counts.cu.  Reached through eodm_debug_set_path(2);
+// kept as the measured answer to "why not tensor cores for small vocabularies" (DESIGN.md section 4.2).
 #include <cuda_runtime.h>
 #include <stdint.h>
 

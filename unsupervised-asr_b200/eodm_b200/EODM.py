@@ -155,6 +155,8 @@ def counts_fwd(table, px, mask, out=None):
     if px.dim() != 3 or px.shape[2] != table.V:
         raise EodmError(_lib.ESHAPE, "px must be [B, T, %d], got %r" % (table.V, tuple(px.shape)))
     B, T, _ = px.shape
+    if px.device.index != table.device:
+        raise EodmError(_lib.EINVAL, "px is on %s but the table lives on cuda:%d" % (px.device, table.device))
     mask = _mask_u8(mask, px.device)
     if tuple(mask.shape) != (B, T):
         raise EodmError(_lib.ESHAPE, "mask must be [%d, %d], got %r" % (B, T, tuple(mask.shape)))
@@ -169,6 +171,8 @@ def counts_fwd(table, px, mask, out=None):
 def counts_bwd(table, px, mask, gS):
     px = _f32c(px, "px")
     B, T, _ = px.shape
+    if px.device.index != table.device:
+        raise EodmError(_lib.EINVAL, "px is on %s but the table lives on cuda:%d" % (px.device, table.device))
     mask = _mask_u8(mask, px.device)
     gS = _f32c(gS, "gS")
     if gS.numel() != table.K:
