@@ -22,7 +22,7 @@
 // operand stages deep.  At the end every CTA writes its sums to a per-slice partial, and a second kernel
 // gathers the K table entries and adds the slices in a fixed order: deterministic, no float atomics.
 //
-// STATUS: correct (3e-6 against the fp64 oracle) but NOT the default path.  One tf32 MMA costs 152 clk whatever
+// STATUS: correct (3e-6 against fp64) but NOT the default path.  One tf32 MMA costs 152 clk whatever
 // its N (tools/ubench_mma.cu), so with N = V = 48 the tensor core runs at a fifth of its rate and timit_c2
 // forward takes 540 us here against 250 us for the walk of counts.cu.  Reached through eodm_debug_set_path(2);
 // kept as the measured answer to "why not tensor cores for small vocabularies" (DESIGN.md section 4.2).
