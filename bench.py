@@ -86,7 +86,7 @@ def run_reference(args):
     r = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
     sec = sum(r["times"]) / len(r["times"])
     val = r["frames"] / sec
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "EODM fwd+bwd frames/sec", "value": val, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -144,23 +144,6 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
 
 
-def pin_to_gpu_numa_node(gpu_index):
-    """Run this rank on the CPUs next to its GPU, so that the pinned host buffers of the end-to-end leg are
-    allocated (first touch) on the GPU's own NUMA node and the copies of 8 ranks do not cross sockets."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return None
-
-
 # ---------------------------------------------------------------------------
 def main():
     args = parse()
@@ -180,7 +163,6 @@ def main():
     assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     comm = None
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
@@ -343,16 +325,27 @@ def main():
             "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
                        "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
-                       "host_cpus_per_rank": numa,
                        "path": "cuda-core trie walk (v2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         comm.close()
         td.destroy_process_group()
 
 
+_JSON_FD = 1
+
+
+def _emit(line):
+    os.write(_JSON_FD, (line + "\n").encode())
+
+
 if __name__ == "__main__":
+    # stdout carries exactly ONE line (the JSON record): libraries that print to fd 1 (NCCL's version banner,
+    # torchrun notices) are sent to stderr instead.
+    sys.stdout.flush()
+    globals()["_JSON_FD"] = os.dup(1)
+    os.dup2(2, 1)
     main()
