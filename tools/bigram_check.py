@@ -49,3 +49,4 @@ if __name__ == "__main__":
     run(4, 33, 384, ragged=True)
     run(16, 64, 1024, time_it=True)
     run(64, 64, 5120, time_it=True)
+    run(512, 64, 5120, time_it=True)
