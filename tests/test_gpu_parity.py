@@ -320,9 +320,11 @@ def test_full_size_properties(eodm):
     assert rel_max(d1[3:4].cpu().numpy(), d_ref) <= TOL
 
 
-@pytest.mark.parametrize("B,T,V,ragged", [(2, 9, 128, False), (3, 40, 256, True), (4, 33, 384, True), (6, 50, 1024, True)])
+@pytest.mark.parametrize("B,T,V,ragged", [(2, 9, 128, False), (3, 40, 256, True), (4, 33, 384, True), (6, 50, 1024, True),
+                                            (20, 64, 1024, True)])
 def test_dense_bigram_tcgen05_vs_oracle(eodm, B, T, V, ragged):
-    """eodm_bigram_dense_fwd/bwd (tcgen05, 3xTF32, TMEM accumulators drained every 16 K-steps) vs the fp64 oracle."""
+    """eodm_bigram_dense_fwd/bwd (TMA-fed tcgen05, 3xTF32, TMEM accumulators drained every 16 K-steps) vs the fp64
+    oracle."""
     dev = _dev()
     logits, mask = O.synth_batch(B, T, V, seed=B, len_lo=2 if ragged else None, scale=3.0)
     px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
