@@ -422,6 +422,30 @@ def test_gather_softmax_and_full_train_step_losses(eodm):
     assert rel_max(lg.grad.cpu().numpy(), O.gather_softmax_vjp(logits, idx, w)) <= TOL
 
 
+@pytest.mark.parametrize("B,T,L,V,sort", [(5, 120, 70, 48, True), (3, 64, 130, 33, False), (4, 300, 400, 40, False),
+                                          (2, 40, 300, 128, True)])
+def test_gather_softmax_shapes(eodm, B, T, L, V, sort):
+    """f1 at other shapes: L not a power of two, L > T (frames gathered many times), unsorted slots, out-of-range
+    indices (clamped like the bounds of the frame axis), V = 33 (generic kernels) and V = 128 (8 float4 per lane)."""
+    dev = _dev()
+    rng = np.random.default_rng(B * 1000 + L)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    idx = rng.integers(0, T, size=(B, L)).astype(np.int32)
+    if sort:
+        idx = np.sort(idx, axis=1)
+    idx[np.arange(L)[None, :] >= rng.integers(L // 2, L + 1, size=B)[:, None]] = 0
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    px = eodm.gather_softmax(lg, torch.tensor(idx, device=dev))
+    assert rel_max(px.detach().cpu().numpy(), O.gather_softmax(logits, idx)) <= TOL
+    w = rng.standard_normal(px.shape).astype(np.float32)
+    (px * torch.tensor(w, device=dev)).sum().backward()
+    g1 = lg.grad.clone()
+    assert rel_max(g1.cpu().numpy(), O.gather_softmax_vjp(logits, idx, w)) <= TOL
+    lg.grad = None
+    (eodm.gather_softmax(lg, torch.tensor(idx, device=dev)) * torch.tensor(w, device=dev)).sum().backward()
+    assert torch.equal(g1, lg.grad)                                   # bit-reproducible
+
+
 def test_dense_bigram_loss_equals_table_loss(eodm):
     """EODM_loss through the dense tcgen05 contraction (gather K entries, loss, scatter, two GEMMs) == EODM_loss
     through the table walk == the oracle, for a bigram table with a duplicated entry."""
@@ -476,3 +500,42 @@ def test_unsupported_shape_is_reported(eodm):
     with pytest.raises(eodm.EodmError) as e:
         eodm.counts_bwd(table, px, m, torch.zeros(100, device=_dev()))
     assert e.value.status == -5
+
+
+def test_device_step_is_cuda_graph_capturable(eodm):
+    """the step (softmax -> counts -> loss, dloss/dS -> VJP) is enqueue-only with no host round trip, so it
+    can be captured once into a CUDA graph and replayed; replays on new inputs are bit-identical to eager launches."""
+    seed, V, n, K, B, T, mixed, dup = CASES[6]
+    ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    sess = eodm.Session(table, py, B, T)
+    lg = torch.tensor(logits, device=dev)
+    m = torch.tensor(mask.astype(np.uint8), device=dev)
+    loss = torch.zeros(1, device=dev)
+    dl = torch.zeros_like(lg)
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        sess.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss.data_ptr(), dl.data_ptr(), side.cuda_stream)   # warm-up
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            sess.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss.data_ptr(), dl.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(99)
+    for trial in range(3):
+        new = torch.tensor(rng.standard_normal(logits.shape).astype(np.float32) * (1 + trial), device=dev)
+        lg.copy_(new)
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        l_graph, d_graph = loss.clone(), dl.clone()
+        loss.zero_(); dl.zero_()
+        st = torch.cuda.current_stream()
+        sess.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss.data_ptr(), dl.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(l_graph, loss) and torch.equal(d_graph, dl)
+        ref = O.eodm_loss_direct(new.cpu().numpy(), mask, ids, n, py)
+        assert abs(float(loss) - ref["loss"]) <= TOL * abs(ref["loss"])
+        assert rel_max(dl.cpu().numpy(), ref["dlogits"]) <= TOL
+    sess.close()
