@@ -50,7 +50,7 @@ struct Mat {
 
 // operand stored [K][MN] if mn-major else [MN][K]
 template <bool A_MN, bool B_MN>
-double run(int M, int N, int K, bool check, int reps, const char* name) {
+double run(int M, int N, int K, bool check, int reps, const char* name, bool two = false) {
   Mat A, B;
   if (A_MN) A.init(K, M, 1u); else A.init(M, K, 1u);
   if (B_MN) B.init(K, N, 2u); else B.init(N, K, 2u);
@@ -61,19 +61,21 @@ double run(int M, int N, int K, bool check, int reps, const char* name) {
   CK(cudaMemset(C, 0, (size_t)(M + 1) * N * 4));
   CUtensorMap ta, tal, tb, tbl;
   bool ok = make_operand_map(&ta, A.x, A.rows, A.cols, A.cols, A_MN, kTM) && make_operand_map(&tal, A.lo, A.rows, A.cols, A.cols, A_MN, kTM) &&
-            make_operand_map(&tb, B.x, B.rows, B.cols, B.cols, B_MN, kTN) && make_operand_map(&tbl, B.lo, B.rows, B.cols, B.cols, B_MN, kTN);
+            make_operand_map(&tb, B.x, B.rows, B.cols, B.cols, B_MN, two ? 128 : kTN) &&
+            make_operand_map(&tbl, B.lo, B.rows, B.cols, B.cols, B_MN, two ? 128 : kTN);
   if (!ok) { printf("tensor map encode failed\n"); exit(1); }
-  Args a;
-  a.M = M; a.N = N; a.K = K; a.scale_out = check ? so : nullptr; a.C = C; a.ldc = N; a.c_row_shift = check ? 1 : 0;
-  a.accumulate = 0; a.m_tiles = (M + kTM - 1) / kTM; a.n_tiles = (N + kTN - 1) / kTN;
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-  CK((launch<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0)));
+  Args a;
+  a.M = M; a.N = N; a.K = K; a.scale_out = check ? so : nullptr; a.C = C; a.ldc = N; a.c_row_shift = check ? 1 : 0;
+  a.accumulate = 0; a.m_tiles = two ? (M + 255) / 256 : (M + kTM - 1) / kTM; a.n_tiles = (N + kTN - 1) / kTN;
+  auto go = [&]() { return two ? launch2<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0) : launch<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0); };
+  CK(go());
   CK(cudaDeviceSynchronize());
   double result = 0;
   if (check) {
     a.accumulate = 1;   // second pass doubles the result
-    CK((launch<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0)));
+    CK(go());
     CK(cudaDeviceSynchronize());
     std::vector<float> ha((size_t)M * K), hb((size_t)N * K), hc((size_t)(M + 1) * N), hs(M);
     CK(cudaMemcpy(ha.data(), A.x, ha.size() * 4, cudaMemcpyDeviceToHost));
@@ -102,7 +104,7 @@ double run(int M, int N, int K, bool check, int reps, const char* name) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) CK((launch<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0)));
+    for (int r = 0; r < reps; ++r) CK(go());
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms;
@@ -127,6 +129,22 @@ int main(int argc, char** argv) {
   worst = fmax(worst, run<false, false>(128, 256, 16, true, 0, "K/K one chunk"));
   worst = fmax(worst, run<true, true>(20 * 128, 8 * 256, 1000, true, 0, "MN/MN 160 tiles (persistent)"));
   printf("worst %.3e -> %s\n", worst, worst < 5e-6 ? "OK" : "FAIL");
+  if (argc > 2 && atoi(argv[2]) > 0) {   // cta_group::2 variants
+    double w2 = 0;
+    w2 = fmax(w2, run<false, false>(128, 256, 16, true, 0, "2-CTA K/K one chunk", true));
+    w2 = fmax(w2, run<false, false>(300, 640, 200, true, 0, "2-CTA K/K", true));
+    w2 = fmax(w2, run<true, false>(288, 640, 200, true, 0, "2-CTA MN/K", true));
+    w2 = fmax(w2, run<false, true>(300, 640, 200, true, 0, "2-CTA K/MN", true));
+    w2 = fmax(w2, run<true, true>(288, 640, 200, true, 0, "2-CTA MN/MN", true));
+    w2 = fmax(w2, run<true, true>(20 * 128, 8 * 256, 1000, true, 0, "2-CTA MN/MN 80 tiles", true));
+    printf("2-CTA worst %.3e -> %s\n", w2, w2 < 5e-6 ? "OK" : "FAIL");
+    worst = fmax(worst, w2);
+    if (timing && w2 < 5e-6) {
+      run<true, true>(5120, 5120, 32768, false, 3, "2-CTA fwd  (MN/MN)", true);
+      run<false, false>(32768, 5120, 5120, false, 3, "2-CTA bwd1 (K/K)", true);
+      run<false, true>(32768, 5120, 5120, false, 3, "2-CTA bwd2 (K/MN)", true);
+    }
+  }
   if (timing) {
     run<true, true>(5120, 5120, 32768, false, 3, "fwd  (MN/MN)");
     run<false, false>(32768, 5120, 5120, false, 3, "bwd1 (K/K)");

@@ -204,14 +204,14 @@ extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B
   // C[u][v] = sum_r Xa[r][u] E[r+1][v]:  rows u, columns v, reduction over frames r; frame NR does not exist (reads 0)
   OperandMaps ma, mb;
   if ((rc = make_maps(&ma, w.Xa, w.Xalo, NR, V, V, true, eodm_tma::kTM)) != EODM_OK) return rc;
-  if ((rc = make_maps(&mb, w.E + V, w.Elo + V, NR - 1, V, V, true, eodm_tma::kTN)) != EODM_OK) return rc;
+  if ((rc = make_maps(&mb, w.E + V, w.Elo + V, NR - 1, V, V, true, eodm_tma::kTM)) != EODM_OK) return rc;
   eodm_tma::Args a;
   a.M = V; a.N = V; a.K = (int)NR;
   a.scale_out = nullptr;
   a.C = C; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
-  a.m_tiles = (V + eodm_tma::kTM - 1) / eodm_tma::kTM; a.n_tiles = (V + eodm_tma::kTN - 1) / eodm_tma::kTN;
-  const cudaError_t e = eodm_tma::launch<true, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st);
-  return e == cudaSuccess ? EODM_OK : fail_launch("gemm3x_tma_kernel", e);
+  a.m_tiles = (V + 255) / 256; a.n_tiles = (V + 255) / 256;   // 256 x 256 tiles, one per CTA pair
+  const cudaError_t e = eodm_tma::launch2<true, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st);
+  return e == cudaSuccess ? EODM_OK : fail_launch("gemm3x_tma2_kernel", e);
 }
 
 extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B, int T, int V, const float* G,
@@ -242,22 +242,22 @@ extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B
   // position 0:  dpx[r][u] = wv[r] * sum_v E[r+1][v] G[u][v]          (every element of dpx is written)
   OperandMaps ma, mb;
   if ((rc = make_maps(&ma, w.E + V, w.Elo + V, NR - 1, V, V, false, eodm_tma::kTM)) != EODM_OK) return rc;
-  if ((rc = make_maps(&mb, G, w.Glo, V, V, V, false, eodm_tma::kTN)) != EODM_OK) return rc;
+  if ((rc = make_maps(&mb, G, w.Glo, V, V, V, false, eodm_tma::kTM)) != EODM_OK) return rc;
   eodm_tma::Args a;
   a.M = (int)NR; a.N = V; a.K = V;
   a.scale_out = w.wv;
   a.C = dpx; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
-  a.m_tiles = (int)((NR + eodm_tma::kTM - 1) / eodm_tma::kTM); a.n_tiles = (V + eodm_tma::kTN - 1) / eodm_tma::kTN;
-  if ((e = eodm_tma::launch<false, false>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
-    return fail_launch("gemm3x_tma_kernel", e);
+  a.m_tiles = (int)((NR + 255) / 256); a.n_tiles = (V + 255) / 256;
+  if ((e = eodm_tma::launch2<false, false>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
+    return fail_launch("gemm3x_tma2_kernel", e);
   // position 1:  dpx[r+1][v] += sum_u Xa[r][u] G[u][v]               (wv is folded into Xa)
   if ((rc = make_maps(&ma, w.Xa, w.Xalo, NR - 1, V, V, false, eodm_tma::kTM)) != EODM_OK) return rc;
-  if ((rc = make_maps(&mb, G, w.Glo, V, V, V, true, eodm_tma::kTN)) != EODM_OK) return rc;
+  if ((rc = make_maps(&mb, G, w.Glo, V, V, V, true, eodm_tma::kTM)) != EODM_OK) return rc;
   a.M = (int)NR - 1; a.scale_out = nullptr;
   a.c_row_shift = 1; a.accumulate = 1;
-  a.m_tiles = (int)((NR - 1 + eodm_tma::kTM - 1) / eodm_tma::kTM);
-  if ((e = eodm_tma::launch<false, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
-    return fail_launch("gemm3x_tma_kernel", e);
+  a.m_tiles = (int)((NR - 1 + 255) / 256);
+  if ((e = eodm_tma::launch2<false, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
+    return fail_launch("gemm3x_tma2_kernel", e);
   return EODM_OK;
 }
 
