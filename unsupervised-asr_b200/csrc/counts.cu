@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/eodm_b200.h"
 #include "kernels.h"
 #include "table.h"
@@ -383,14 +385,26 @@ struct BwdWalk {
   }
 };
 
+// out[r] = init + sum over the `count` (>= 1) nodes that follow in the stream of
+//          P[phone][row r] * (g of the node + the same sum over its children).
+// `out` is ASSIGNED: the first node folds `init` into its FMA, so no level ever spends R moves on initialising a sum
+// (the deep, thin tries of 4- and 5-gram tables are bound by issue slots, not by shared memory).
+// `off` is the trie's level -> column offset table, copied to registers once per trie.
 template <int L, int DEPTH, int R>
-__device__ __forceinline__ void bwd_visit(BwdWalk& w, const TrieArg& tr, const float* Pl, int ld, float (&out)[R],
-                                          int count) {
+__device__ __forceinline__ void bwd_visit(BwdWalk& w, const int (&off)[EODM_MAX_N], const float* Pl, int ld, float (&out)[R],
+                                          float init, int count) {
   if constexpr (L + 1 == DEPTH) {
     // deepest level: nothing but n-gram ends.  Two per trip, all loads before the FMAs, so that a warp keeps
     // 2R shared-memory reads in flight (the walk is bound by shared-memory wavefronts, not by issue).
-    const float* base = Pl + tr.off[L];
-    int c = 0;
+    const float* base = Pl + off[L];
+    {
+      const uint2 e = w.next();
+      const float g = __uint_as_float(e.y);
+      const float* row = base + EODM_NODE_PHONE(e.x) * ld;
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, init);
+    }
+    int c = 1;
 #pragma unroll 1
     for (; c + 2 <= count; c += 2) {
       const uint2 e0 = w.next();
@@ -416,26 +430,26 @@ __device__ __forceinline__ void bwd_visit(BwdWalk& w, const TrieArg& tr, const f
       for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, out[r]);
     }
     return;
-  }
-#pragma unroll 1
-  for (int c = 0; c < count; ++c) {
-    const uint2 e = w.next();
-    const float g = __uint_as_float(e.y);  // 0 unless an n-gram ends here
-    const float* row = Pl + EODM_NODE_PHONE(e.x) * ld + tr.off[L];
-    if constexpr (L + 1 < DEPTH) {
+  } else {
+    auto visit = [&](auto first_tag) {
+      constexpr bool kFirst = decltype(first_tag)::value;
+      const uint2 e = w.next();
+      const float g = __uint_as_float(e.y);  // 0 unless an n-gram ends here
+      const float* row = Pl + EODM_NODE_PHONE(e.x) * ld + off[L];
       const int nc = EODM_NODE_NCHILD(e.x);
       if (nc) {
         float s[R];
+        bwd_visit<L + 1, DEPTH, R>(w, off, Pl, ld, s, g, nc);
 #pragma unroll
-        for (int r = 0; r < R; ++r) s[r] = g;
-        bwd_visit<L + 1, DEPTH, R>(w, tr, Pl, ld, s, nc);
+        for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], s[r], kFirst ? init : out[r]);
+      } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], s[r], out[r]);
-        continue;
+        for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, kFirst ? init : out[r]);
       }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], g, out[r]);
+    };
+    visit(std::true_type{});
+#pragma unroll 1
+    for (int c = 1; c < count; ++c) visit(std::false_type{});
   }
 }
 
@@ -474,6 +488,9 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
       for (int j = 0; j < n; ++j) {
         const TrieArg& tr = args.trie[j];
         w.ng = tr.ng;
+        int off[EODM_MAX_N];
+#pragma unroll
+        for (int l = 0; l < EODM_MAX_N; ++l) off[l] = tr.off[l];
         int u_lo, u_hi;
         warp_unit_range(tr, warp, u_lo, u_hi);
         if (lane < 2) side_root[warp][lane] = -1;
@@ -504,20 +521,22 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
           const int n_self = max(0, min(hi, (int)(rt.y + rt.z)) - lo);
           const int n_sub = (hi - lo) - n_self;
           cur_root = (int)rt.x;
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = 0.f;
+          float gs = 0.f;
           if (n_self) {  // n-grams that are just (root): d/dP[root] = g * mask
             const uint32_t g0 = __ldg(&tr.units[lo].leaf_cursor);
-            float gs = 0.f;
             for (int k = 0; k < n_self; ++k) gs += __ldg(tr.g + g0 + k);
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = gs;
           }
+          bool walked = false;
           if constexpr (DEPTH > 1) {
             if (n_sub) {
               w.seek(__ldg(&tr.units[lo + n_self].node_cursor));
-              bwd_visit<1, DEPTH, R>(w, tr, Pl, ld, acc, n_sub);
+              bwd_visit<1, DEPTH, R>(w, off, Pl, ld, acc, gs, n_sub);
+              walked = true;
             }
+          }
+          if (!walked) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = gs;
           }
           // a root cut by a warp boundary goes through the side buffer and is added in warp order
           flush(lo == (int)rt.y && hi == (int)(rt.y + rt.w));
