@@ -255,6 +255,7 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   int u_lo, u_hi;
   warp_unit_range(tr, warp, u_lo, u_hi);
+  const int ri0 = (u_lo < u_hi) ? root_of_unit(tr, u_lo) : tr.n_roots;
   FwdWalk w;
   w.nodes = tr.nodes;
   w.stage = stage + warp * kStageLeaves * kStageLd;
@@ -292,7 +293,7 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
     // roots whose units intersect this warp's share; within a root the n-grams ending at the root come first,
     // then its depth-2 subtrees, contiguous in the node stream
 #pragma unroll 1
-    for (int ri = (u_lo < u_hi) ? root_of_unit(tr, u_lo) : tr.n_roots; ri < tr.n_roots; ++ri) {
+    for (int ri = ri0; ri < tr.n_roots; ++ri) {
       const uint4 rt = __ldg(reinterpret_cast<const uint4*>(tr.roots) + ri);
       if ((int)rt.y >= u_hi) break;
       const int lo = max(u_lo, (int)rt.y), hi = min(u_hi, (int)(rt.y + rt.w));
@@ -467,9 +468,19 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
   float* wm = dP + V * ldo;               // [TS+n-1]  windows row0-(n-1) .. row0+TS-1
   float* side = wm + (TS + n - 1);        // [kWarps][2][TS]
   __shared__ int side_root[kWarps][2];
+  __shared__ int share[kWarps][EODM_MAX_N][3];   // per warp and trie: first unit, end unit, first root (tile-independent)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* Pl = Ps + lane;
   BwdWalk w;
+  if (lane < n) {   // the binary searches are chains of dependent global loads: once per kernel, not once per tile
+    const TrieArg& tr = args.trie[lane];
+    int lo, hi;
+    warp_unit_range(tr, warp, lo, hi);
+    share[warp][lane][0] = lo;
+    share[warp][lane][1] = hi;
+    share[warp][lane][2] = lo < hi ? root_of_unit(tr, lo) : tr.n_roots;
+  }
+  __syncwarp();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * ts;
@@ -491,8 +502,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
         int off[EODM_MAX_N];
 #pragma unroll
         for (int l = 0; l < EODM_MAX_N; ++l) off[l] = tr.off[l];
-        int u_lo, u_hi;
-        warp_unit_range(tr, warp, u_lo, u_hi);
+        const int u_lo = share[warp][j][0], u_hi = share[warp][j][1];
         if (lane < 2) side_root[warp][lane] = -1;
         // the lane's output rows are row0 + lane + 32 r; in trie j they come from windows row - j
         float wmv[R];
@@ -514,7 +524,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
           }
         };
 #pragma unroll 1
-        for (int ri = (u_lo < u_hi) ? root_of_unit(tr, u_lo) : tr.n_roots; ri < tr.n_roots; ++ri) {
+        for (int ri = share[warp][j][2]; ri < tr.n_roots; ++ri) {
           const uint4 rt = __ldg(reinterpret_cast<const uint4*>(tr.roots) + ri);
           if ((int)rt.y >= u_hi) break;
           const int lo = max(u_lo, (int)rt.y), hi = min(u_hi, (int)(rt.y + rt.w));
