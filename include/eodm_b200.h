@@ -84,6 +84,12 @@ size_t eodm_workspace_bytes(const eodm_table* t, int B, int T);
 int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
                     float* S, float* N, void* ws, void* stream);
 
+/* Legacy per-device partial sums (models/EODM.py:28-52, summed across devices on the host and divided there,
+ * main_es.py:135,331-335): S as above, un-normalised, and Kw = sum_{b, t <= T-n} mask[b,t] (f32[1]) -- the mask is
+ * cut to the window starts here, unlike the denominator N of EODM_loss.  Always the trie walk. */
+int eodm_counts_partial(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                        float* S, float* Kw, void* ws, void* stream);
+
 /* dpx[b,s,v] = sum_{z,j: ids[z,j]=v} gS[z] * mask[b,s-j] * prod_{j'!=j}(px[b,s-j+j',ids[z,j']] + 1e-15)
  * i.e. the vector-Jacobian product TF autodiff yields for the expression above
  * (main_EODM.py:168 through EODM.py:18-20).  dpx f32[B][T][V] is overwritten. */

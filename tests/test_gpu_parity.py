@@ -539,3 +539,30 @@ def test_device_step_is_cuda_graph_capturable(eodm):
         assert abs(float(loss) - ref["loss"]) <= TOL * abs(ref["loss"])
         assert rel_max(dl.cpu().numpy(), ref["dlogits"]) <= TOL
     sess.close()
+
+
+def test_legacy_partial_sums(eodm):
+    """SURVEY 8a row a6 -- models/EODM.py:28-52: un-normalised (pz, K) per device, K = the mask cut to the window
+    starts; two "devices" (halves of the batch) summed on the host and divided as main_es.py:331-335 does."""
+    dev = _dev()
+    rng = np.random.default_rng(21)
+    B, T, V, L, n, K = 6, 80, 40, 30, 3, 500
+    ids, py = O.synth_table(V, n, K, seed=5)
+    kernel = O.ids_to_kernel(ids, V)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    aligns = np.sort(rng.integers(1, T, size=(B, L)), axis=1).astype(np.int32)
+    aligns[np.arange(L)[None, :] >= rng.integers(n, L + 1, size=B)[:, None]] = 0
+    px = O.gather_softmax(logits, aligns)
+    mask = aligns > 0
+    S_ref, _ = O.counts_fwd(px, mask, ids, n)
+    K_ref = float(mask[:, :L - n + 1].sum())
+    lg = torch.tensor(logits, device=dev)
+    pz, Kv = eodm.EODM(lg, torch.tensor(aligns, device=dev), kernel)
+    assert pz.shape == (K,) and Kv.shape == (K,)
+    assert np.abs(pz.cpu().numpy() - S_ref).max() <= TOL * np.abs(S_ref).max()
+    assert torch.all(Kv == K_ref)
+    parts = [eodm.EODM(lg[h], torch.tensor(aligns[h], device=dev), kernel) for h in (slice(0, 3), slice(3, 6))]
+    pz_sum = sum(p for p, _ in parts)
+    K_sum = sum(k for _, k in parts)
+    assert torch.all(K_sum == K_ref)
+    assert rel_max((pz_sum / K_sum).cpu().numpy(), S_ref / K_ref) <= TOL

@@ -85,6 +85,142 @@ __global__ void __launch_bounds__(512, 1) k_lds(const uint2* __restrict__ ng, fl
   if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
 }
 
+__global__ void __launch_bounds__(512, 1) k_lds4(const uint2* __restrict__ ng, float* out, long long* clk, int bwd) {
+  extern __shared__ float Ps[];  // [V][ld]
+  const int ld = 32 * R + 4;
+  for (int i = threadIdx.x; i < V * ld; i += 512) Ps[i] = 1.0f + 1e-6f * i;
+  __shared__ float stage[16][16 * 33];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* Pl = Ps + 4 * lane;
+  float qp[R], o[R];
+  for (int r = 0; r < R; ++r) { qp[r] = 1.f + r; o[r] = 0.f; }
+  float accum = 0.f;
+  int pend = 0;
+  const long long t0 = clock64();
+  for (int rep = 0; rep < REP; ++rep) {
+    const uint2* p = ng + warp * NODES;
+    uint2 ahead = __ldg(p);
+#pragma unroll 1
+    for (int c = 0; c < NODES; c += 2) {
+      const uint2 e0 = ahead, e1 = __ldg(p + c + 1);
+      ahead = __ldg(p + c + 2);
+      const float* r0 = Pl + (e0.x & 0xffff) * ld;
+      const float* r1 = Pl + (e1.x & 0xffff) * ld;
+      float a0[R], a1[R];
+#pragma unroll
+      for (int r = 0; r < R; r += 4) { const float4 v = *reinterpret_cast<const float4*>(r0 + 32 * r); a0[r] = v.x; a0[r + 1] = v.y; a0[r + 2] = v.z; a0[r + 3] = v.w; }
+#pragma unroll
+      for (int r = 0; r < R; r += 4) { const float4 v = *reinterpret_cast<const float4*>(r1 + 32 * r); a1[r] = v.x; a1[r + 1] = v.y; a1[r + 2] = v.z; a1[r + 3] = v.w; }
+      if (bwd) {
+        const float g0 = __uint_as_float(e0.y), g1 = __uint_as_float(e1.y);
+#ifdef USE_FFMA2
+#pragma unroll
+        for (int r = 0; r < R; r += 2) fma2(o[r], o[r + 1], a0[r], a0[r + 1], g0, o[r], o[r + 1]);
+#pragma unroll
+        for (int r = 0; r < R; r += 2) fma2(o[r], o[r + 1], a1[r], a1[r + 1], g1, o[r], o[r + 1]);
+#else
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = fmaf(a0[r], g0, o[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = fmaf(a1[r], g1, o[r]);
+#endif
+      } else {
+        float s0 = qp[0] * a0[0], s1 = qp[0] * a1[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) { s0 = fmaf(qp[r], a0[r], s0); s1 = fmaf(qp[r], a1[r], s1); }
+        stage[warp][pend * 33 + lane] = s0;
+        stage[warp][(pend + 1) * 33 + lane] = s1;
+        pend += 2;
+        if (pend == 16) {
+          __syncwarp();
+          const float* s = &stage[warp][(lane & 15) * 33 + (lane >> 4) * 16];
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v += s[k];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          accum += v;
+          pend = 0;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = accum;
+  for (int r = 0; r < R; ++r) s += o[r];
+  out[blockIdx.x * 512 + threadIdx.x] = s;
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+__global__ void __launch_bounds__(512, 1) k_lds2(const uint2* __restrict__ ng, float* out, long long* clk, int bwd) {
+  extern __shared__ float Ps[];  // [V][ld]
+  const int ld = 32 * R + 2;
+  for (int i = threadIdx.x; i < V * ld; i += 512) Ps[i] = 1.0f + 1e-6f * i;
+  __shared__ float stage[16][16 * 33];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* Pl = Ps + 2 * lane;
+  float qp[R], o[R];
+  for (int r = 0; r < R; ++r) { qp[r] = 1.f + r; o[r] = 0.f; }
+  float accum = 0.f;
+  int pend = 0;
+  const long long t0 = clock64();
+  for (int rep = 0; rep < REP; ++rep) {
+    const uint2* p = ng + warp * NODES;
+    uint2 ahead = __ldg(p);
+#pragma unroll 1
+    for (int c = 0; c < NODES; c += 2) {
+      const uint2 e0 = ahead, e1 = __ldg(p + c + 1);
+      ahead = __ldg(p + c + 2);
+      const float* r0 = Pl + (e0.x & 0xffff) * ld;
+      const float* r1 = Pl + (e1.x & 0xffff) * ld;
+      float a0[R], a1[R];
+#pragma unroll
+      for (int r = 0; r < R; r += 2) { const float2 v = *reinterpret_cast<const float2*>(r0 + 32 * r); a0[r] = v.x; a0[r + 1] = v.y; }
+#pragma unroll
+      for (int r = 0; r < R; r += 2) { const float2 v = *reinterpret_cast<const float2*>(r1 + 32 * r); a1[r] = v.x; a1[r + 1] = v.y; }
+      if (bwd) {
+        const float g0 = __uint_as_float(e0.y), g1 = __uint_as_float(e1.y);
+#ifdef USE_FFMA2
+#pragma unroll
+        for (int r = 0; r < R; r += 2) fma2(o[r], o[r + 1], a0[r], a0[r + 1], g0, o[r], o[r + 1]);
+#pragma unroll
+        for (int r = 0; r < R; r += 2) fma2(o[r], o[r + 1], a1[r], a1[r + 1], g1, o[r], o[r + 1]);
+#else
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = fmaf(a0[r], g0, o[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = fmaf(a1[r], g1, o[r]);
+#endif
+      } else {
+        float s0 = qp[0] * a0[0], s1 = qp[0] * a1[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) { s0 = fmaf(qp[r], a0[r], s0); s1 = fmaf(qp[r], a1[r], s1); }
+        stage[warp][pend * 33 + lane] = s0;
+        stage[warp][(pend + 1) * 33 + lane] = s1;
+        pend += 2;
+        if (pend == 16) {
+          __syncwarp();
+          const float* s = &stage[warp][(lane & 15) * 33 + (lane >> 4) * 16];
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v += s[k];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          accum += v;
+          pend = 0;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = accum;
+  for (int r = 0; r < R; ++r) s += o[r];
+  out[blockIdx.x * 512 + threadIdx.x] = s;
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
 __global__ void __launch_bounds__(512, 1) k_tmem(const uint2* __restrict__ ng, float* out, long long* clk, int bwd) {
   __shared__ uint32_t slot;
   __shared__ float stage[16][16 * 33];
@@ -265,19 +401,23 @@ int main() {
   for (int i = 0; i < 16 * NODES + 16; ++i) { h = h * 1664525u + 1013904223u; ng[i].x = (h >> 8) % 47 + 1; ng[i].y = 0x3f800000u; }
   const int ld = (32 * R + 2) | 1;
   cudaFuncSetAttribute(k_lds, cudaFuncAttributeMaxDynamicSharedMemorySize, V * ld * 4);
+  cudaFuncSetAttribute(k_lds4, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (32 * R + 4) * 4);
+  cudaFuncSetAttribute(k_lds2, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (32 * R + 4) * 4);
   for (int bwd = 0; bwd < 2; ++bwd) {
-    for (int which = 0; which < 3; ++which) {
+    for (int which = 0; which < 5; ++which) {
       for (int it = 0; it < 2; ++it) {
         if (which == 0) k_lds<<<148, 512, V * ld * 4>>>(ng, out, clk, bwd);
         else if (which == 1) k_tmem<<<148, 512>>>(ng, out, clk, bwd);
-        else k_tmem4<<<148, 512>>>(ng, out, clk, bwd);
+        else if (which == 2) k_tmem4<<<148, 512>>>(ng, out, clk, bwd);
+        else if (which == 3) k_lds4<<<148, 512, V * (32 * R + 4) * 4>>>(ng, out, clk, bwd);
+        else k_lds2<<<148, 512, V * (32 * R + 4) * 4>>>(ng, out, clk, bwd);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
       double c = 0; for (int b = 0; b < 148; ++b) c += clk[b]; c /= 148;
       const double per_node_warp = c / (double)(REP * NODES);       // clk for one node on all 16 warps = 16 node-warps
       printf("%s leaf loop, %s: %.2f clk per node per warp-slot (16 warps in flight) -> %.1f (node,window) pairs/clk/SM, out=%g\n",
-             bwd ? "bwd" : "fwd", which == 2 ? "TMEM x8, 4 nodes per wait" : which ? "TMEM x8" : "LDS  R=8", per_node_warp / 16.0, 16.0 * 32 * R / per_node_warp, out[0]);
+             bwd ? "bwd" : "fwd", which == 4 ? "LDS.64 R=8" : which == 3 ? "LDS.128 R=8" : which == 2 ? "TMEM x8, 4 nodes per wait" : which ? "TMEM x8" : "LDS  R=8", per_node_warp / 16.0, 16.0 * 32 * R / per_node_warp, out[0]);
     }
   }
   return 0;

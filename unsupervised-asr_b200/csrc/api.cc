@@ -73,7 +73,17 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
   if (use_tensor_fwd(t))
     return eodm_tc_fwd_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t), (cudaStream_t)stream);
-  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, ws, (cudaStream_t)stream);
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream);
+}
+
+// The reference's older multi-device step (models/EODM.py:28-52, main_es.py:135,331-335) returns UN-normalised
+// partial sums per device: S as above and, as denominator, the mask summed over window starts only.
+extern "C" int eodm_counts_partial(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
+                                   float* Kw, void* ws, void* stream) {
+  int rc = check_batch(t, px, mask, B, T);
+  if (rc != EODM_OK) return rc;
+  REQUIRE(S && Kw && ws, EODM_EINVAL, "null pointer");
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, nullptr, Kw, ws, (cudaStream_t)stream);
 }
 
 extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,

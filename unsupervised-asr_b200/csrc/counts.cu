@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __
                                                                  const int* __restrict__ part_cnt, int n_cta,
                                                                  int n_leaves, const int32_t* __restrict__ perm,
                                                                  const int32_t* __restrict__ order0, int n_order0,
-                                                                 float* __restrict__ S, float* __restrict__ N) {
+                                                                 float* __restrict__ S, float* __restrict__ N,
+                                                                 float* __restrict__ W) {
   __shared__ float red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int leaf = blockIdx.x * 32 + x;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __
     }
     if (i < n_order0) S[order0[i]] = (float)cw;
     if (i == 0 && N) N[0] = (float)cn;
+    if (i == 0 && W) W[0] = (float)cw;   // the truncated denominator of the legacy partial sums (models/EODM.py:49-50)
   }
 }
 
@@ -734,7 +736,7 @@ static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, flo
 }
 
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           void* ws, cudaStream_t st) {
+                           float* W, void* ws, cudaStream_t st) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   const int n_leaves = t->trie[0].n_leaves;
@@ -778,7 +780,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   if (fg < 1) fg = 1;
   const int fb = 256;
   eodm_counts_finish_kernel<<<fg, fb, 0, st>>>(part, cnt, tl.grid, n_leaves, t->trie[0].perm, t->d_order0,
-                                               t->n_order0, S, N);
+                                               t->n_order0, S, N, W);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_counts_finish_kernel launch failed: %s", cudaGetErrorString(e));

@@ -11,7 +11,7 @@ struct eodm_table;
 // counts.cu -- CUDA-core trie path
 size_t eodm_counts_workspace_bytes(const eodm_table* t);
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           void* ws, cudaStream_t st);
+                           float* W, void* ws, cudaStream_t st);   // W (optional): number of valid window starts
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
                            float* dpx, void* ws, cudaStream_t st);
 

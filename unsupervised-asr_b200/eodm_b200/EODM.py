@@ -168,6 +168,41 @@ def counts_fwd(table, px, mask, out=None):
     return out
 
 
+def counts_partial(table, px, mask):
+    """Legacy per-device partial sums (models/EODM.py:28-52): -> (S f32[K] un-normalised, Kw f32[1] = number of
+    valid window starts, the denominator the reference cuts to `[:, :T-n+1]` in this variant)."""
+    px = _f32c(px, "px")
+    if px.dim() != 3 or px.shape[2] != table.V:
+        raise EodmError(_lib.ESHAPE, "px must be [B, T, %d], got %r" % (table.V, tuple(px.shape)))
+    B, T, _ = px.shape
+    if px.device.index != table.device:
+        raise EodmError(_lib.EINVAL, "px is on %s but the table lives on cuda:%d" % (px.device, table.device))
+    mask = _mask_u8(mask, px.device)
+    S = torch.empty(table.K, dtype=torch.float32, device=px.device)
+    Kw = torch.empty(1, dtype=torch.float32, device=px.device)
+    ws = table.workspace(B, T)
+    check(lib.eodm_counts_partial(table._h, _ptr(px), _ptr(mask), B, T, _ptr(S), _ptr(Kw), _ptr(ws), _stream()))
+    return S, Kw
+
+
+def EODM(logits, aligns, kernel):
+    """The reference's older per-device step, models/EODM.py:28-52 (called as model.EODM(logits, aligns, kernel) in
+    main_es.py:135): gather the frames at `aligns`, softmax, and return the UN-normalised `(pz f32[K], K f32[K])`
+    that the host sums over devices and divides (main_es.py:331-335).  `kernel` is the dense one-hot kernel of
+    ngram2kernel (or an already built PNgram / NgramTable).  Forward only, as in the reference's use."""
+    from . import tools as _tools
+    if isinstance(kernel, PNgram):
+        table = kernel.table
+    elif isinstance(kernel, NgramTable):
+        table = kernel
+    else:
+        table = NgramTable.from_dense(np.asarray(kernel), device=logits.device.index)
+    al = torch.as_tensor(aligns).to(logits.device)
+    px = _tools.gather_softmax(logits.detach(), al)
+    S, Kw = counts_partial(table, px, al > 0)
+    return S, Kw.expand(table.K)
+
+
 def counts_bwd(table, px, mask, gS):
     px = _f32c(px, "px")
     B, T, _ = px.shape

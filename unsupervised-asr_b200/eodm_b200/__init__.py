@@ -8,6 +8,7 @@ from .tools import (load_vocab, read_ngram, ngram2kernel, ngram_ids, gather_soft
                     get_N_gram, get_dataset_ngram,
                     frames_constrain_loss)
 from .EODM import (P_Ngram, EODM_loss, PNgram, NgramTable, softmax_fwd, softmax_bwd, counts_fwd, counts_bwd,  # noqa: F401
-                   loss_from_counts, bigram_dense_fwd, bigram_dense_bwd, EODM_loss_dense_bigram)
+                   loss_from_counts, bigram_dense_fwd, bigram_dense_bwd, EODM_loss_dense_bigram, EODM,
+                   counts_partial)
 from .session import Session  # noqa: F401
 from . import dist, synth  # noqa: F401

@@ -49,6 +49,7 @@ SIGNATURES = {
     "eodm_table_to_dense": (_i, [_p, _p]),
     "eodm_workspace_bytes": (C.c_size_t, [_p, _i, _i]),
     "eodm_counts_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "eodm_counts_partial": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_counts_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_loss_from_counts": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _p]),
     "eodm_softmax_fwd": (_i, [_p, C.c_int64, _i, _p, _p]),
