@@ -157,6 +157,23 @@ int eodm_comm_unique_id(char id_out[128]);
 int eodm_comm_init(void** comm_out, int nranks, const char id[128], int rank);
 int eodm_comm_destroy(void* comm);
 
+/* ---- the exchange fused with the loss over NVLink peer memory (csrc/peer.cu) ----
+ * Alternative to eodm_allreduce_counts + eodm_loss_from_counts for one process per GPU on one node: each rank creates
+ * a peer-visible buffer (handle_out: 64-byte CUDA IPC handle), the host gathers the handles of all ranks by any side
+ * channel and attaches them, and from then on ONE kernel per step publishes the rank's partial counts, waits for
+ * its peers and forms the global counts (added in rank order: identical bits on every rank), loss and dloss/dS.
+ * Replaces the cross-device sum of models/EODM.py:28-52 / main_es.py:331-335 like eodm_allreduce_counts does. */
+typedef struct eodm_peer eodm_peer;
+int eodm_peer_create(int world, int rank, int K, eodm_peer** out, char handle_out[64]);
+int eodm_peer_attach(eodm_peer* p, const char* handles /* world x 64 bytes, in rank order */);
+void eodm_peer_destroy(eodm_peer* p);
+/* counts: this rank's packed [S_r (K), N_r] on the device; loss f32[1]; gS f32[K] or NULL; counts_out f32[K+1] or NULL.
+ * Collective, enqueue-only, CUDA-graph capturable (the step number lives on the device). */
+int eodm_peer_loss(eodm_peer* p, const float* counts, const float* py, float eps, float* loss, float* gS,
+                   float* counts_out, void* stream);
+/* 1 if an earlier eodm_peer_loss gave up waiting (~2 s) for a peer and wrote NaN; synchronises the device. */
+int eodm_peer_failed(eodm_peer* p);
+
 /* ---- one-call step with HOST buffers (what a plugin user times end to end) ---- */
 /* Owns device buffers, pinned staging and a stream for batches up to [maxB, maxT]. */
 typedef struct eodm_session eodm_session;
@@ -164,6 +181,8 @@ int eodm_session_create(const eodm_table* t, const float* py_host, int maxB, int
 void eodm_session_destroy(eodm_session* s);
 /* The stream the session enqueues on (a cudaStream_t). */
 void* eodm_session_stream(eodm_session* s);
+/* Use a peer group (above) instead of the `comm` argument for the exchange of the following steps; NULL to undo. */
+int eodm_session_set_peer(eodm_session* s, eodm_peer* peer);
 /* The same step on DEVICE buffers the caller already holds (a TF custom op, a CUDA graph):
  * softmax -> counts -> [allreduce] -> loss -> counts VJP -> softmax VJP, enqueued on `stream`
  * with the session's scratch; no copies, no synchronisation.  loss f32[1], dlogits

@@ -46,8 +46,26 @@ def _worker(rank, world, port, out):
         dl = np.empty_like(logits[lo:hi])
         loss2 = sess.loss(np.ascontiguousarray(logits[lo:hi]), np.ascontiguousarray(mask[lo:hi]), dl, comm=comm)
         torch.cuda.synchronize()
-        out.put((rank, lo, hi, float(loss.detach()), lg.grad.cpu().numpy(), loss2, dl))
+        # the same step with the exchange fused into the loss kernel over peer memory (csrc/peer.cu)
+        group = E.dist.PeerGroup.from_torch_distributed(K)
+        E.dist.attach(conv_op, group)
+        lg3 = torch.tensor(logits[lo:hi], device=dev, requires_grad=True)
+        losses3 = []
+        for _ in range(3):                                   # both slots and a reused one
+            lg3.grad = None
+            loss3 = E.EODM_loss(lg3, torch.tensor(mask[lo:hi], device=dev), conv_op, K, py)
+            loss3.backward()
+            losses3.append(float(loss3.detach()))
+        sess.set_peer(group)
+        dl4 = np.empty_like(logits[lo:hi])
+        loss4 = sess.loss(np.ascontiguousarray(logits[lo:hi]), np.ascontiguousarray(mask[lo:hi]), dl4, comm=None)
+        torch.cuda.synchronize()
+        assert not group.failed()
+        out.put((rank, lo, hi, float(loss.detach()), lg.grad.cpu().numpy(), loss2, dl,
+                 losses3, lg3.grad.cpu().numpy(), loss4, dl4))
         td.barrier()
+        sess.close()
+        group.close()
         comm.close()
     finally:
         td.destroy_process_group()
@@ -76,8 +94,13 @@ def test_two_gpu_sharded_step_matches_single_gpu(eodm):
     loss = E.EODM_loss(lg, torch.tensor(mask, device="cuda:0"), conv_op, K, py)
     loss.backward()
     ref_g = lg.grad.cpu().numpy()
-    for rank, lo, hi, l, g, l2, g2 in res:
+    for rank, lo, hi, l, g, l2, g2, l3s, g3, l4, g4 in res:
         assert abs(l - float(loss)) <= 1e-6 * abs(float(loss))        # NCCL sum order != 1-GPU order: 1e-6, not bit-exact
         assert np.abs(g - ref_g[lo:hi]).max() <= 1e-5 * np.abs(ref_g).max()
         assert abs(l2 - l) <= 1e-6 * abs(l) and np.abs(g2 - g).max() <= 1e-6 * np.abs(ref_g).max()
+        # peer-memory exchange: same numbers, and the same bits step after step
+        assert l3s[0] == l3s[1] == l3s[2] and abs(l3s[0] - l) <= 1e-6 * abs(l)
+        assert np.abs(g3 - ref_g[lo:hi]).max() <= 1e-5 * np.abs(ref_g).max()
+        assert l4 == l3s[0] and np.array_equal(g4, g3)
     assert res[0][3] == res[1][3]                                     # both ranks hold the same loss bits
+    assert res[0][7] == res[1][7] and res[0][9] == res[1][9]          # ... with the peer exchange too (rank-order sum)

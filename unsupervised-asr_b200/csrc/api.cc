@@ -237,6 +237,7 @@ struct eodm_session {
   float *py, *gS, *loss;
   uint8_t* mask;
   void* ws;
+  eodm_peer* peer;   // when set: the exchange + loss run as one kernel over peer memory (peer.cu)
 };
 
 static void session_free(eodm_session* s) {
@@ -304,6 +305,23 @@ extern "C" void eodm_session_destroy(eodm_session* s) { session_free(s); }
 
 extern "C" void* eodm_session_stream(eodm_session* s) { return s ? (void*)s->st : nullptr; }
 
+extern "C" int eodm_session_set_peer(eodm_session* s, eodm_peer* peer) {
+  REQUIRE(s, EODM_EINVAL, "null pointer");
+  s->peer = peer;
+  return EODM_OK;
+}
+
+// exchange (if any) + loss + dloss/dS from this rank's packed counts
+static int session_exchange_and_loss(eodm_session* s, float* counts, void* comm, float* loss, bool need_grad,
+                                     cudaStream_t st) {
+  const int K = s->t->K;
+  if (s->peer) return eodm_peer_loss(s->peer, counts, s->py, 1e-15f, loss, need_grad ? s->gS : nullptr, nullptr, st);
+  int rc = EODM_OK;
+  if (comm) rc = eodm_allreduce_counts(comm, counts, K, counts + K, st);
+  if (rc == EODM_OK) rc = eodm_loss_launch(counts, counts + K, s->py, K, 1e-15f, loss, need_grad ? s->gS : nullptr, st);
+  return rc;
+}
+
 extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, const uint8_t* mask, int B, int T,
                                         void* comm, float* loss, float* dlogits, void* stream) {
   REQUIRE(s && logits && mask && loss, EODM_EINVAL, "null pointer");
@@ -317,8 +335,7 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   float* N = s->counts + t->K;
   int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
   if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);
-  if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, S, t->K, N, st);
-  if (rc == EODM_OK) rc = eodm_loss_launch(S, N, s->py, t->K, 1e-15f, loss, dlogits ? s->gS : nullptr, st);
+  if (rc == EODM_OK) rc = session_exchange_and_loss(s, s->counts, comm, loss, dlogits != nullptr, st);
   if (rc == EODM_OK && dlogits) rc = eodm_counts_bwd(t, s->px, mask, B, T, s->gS, s->dpx, s->ws, st);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(s->px, s->dpx, rows, t->V, dlogits, st);
   return rc;
@@ -352,9 +369,8 @@ static int session_loss_pipelined(eodm_session* s, const float* logits_host, con
     if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
   }
   if (e == cudaSuccess && rc == EODM_OK) rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
-  if (e == cudaSuccess && rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, s->counts, K, s->counts + K, s->st);
   if (e == cudaSuccess && rc == EODM_OK)
-    rc = eodm_loss_launch(s->counts, s->counts + K, s->py, K, 1e-15f, s->loss, dlogits_host ? s->gS : nullptr, s->st);
+    rc = session_exchange_and_loss(s, s->counts, comm, s->loss, dlogits_host != nullptr, s->st);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(s->ev_done, s->st);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->copy_st, s->ev_done, 0);
   if (e == cudaSuccess && rc == EODM_OK)

@@ -254,10 +254,13 @@ class _EodmLossFn(torch.autograd.Function):
         logits = _f32c(logits, "_logits")
         px = softmax_fwd(logits)                                   # models/EODM.py:15
         counts = counts_fwd(table, px, mask)                       # :14,18-20 (numerator and N)
-        if comm is not None:
-            comm.allreduce_counts(counts, table.K)                 # batch-sharded step
         need = logits.requires_grad
-        loss, gS = loss_from_counts(counts, py, table.K, need)     # :20-23
+        if comm is not None and hasattr(comm, "fused_loss"):       # batch-sharded step, exchange fused with the loss
+            loss, gS, _ = comm.fused_loss(counts, py, need)
+        else:
+            if comm is not None:
+                comm.allreduce_counts(counts, table.K)             # batch-sharded step
+            loss, gS = loss_from_counts(counts, py, table.K, need)  # :20-23
         ctx.table, ctx.mask = table, mask
         ctx.save_for_backward(px, gS if need else torch.empty(0, device=px.device))
         ctx.counts = counts

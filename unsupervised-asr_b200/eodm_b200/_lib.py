@@ -49,6 +49,12 @@ SIGNATURES = {
     "eodm_table_to_dense": (_i, [_p, _p]),
     "eodm_workspace_bytes": (C.c_size_t, [_p, _i, _i]),
     "eodm_counts_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "eodm_peer_create": (_i, [_i, _i, _i, _p, _p]),
+    "eodm_peer_attach": (_i, [_p, _p]),
+    "eodm_peer_destroy": (None, [_p]),
+    "eodm_peer_loss": (_i, [_p, _p, _p, C.c_float, _p, _p, _p, _p]),
+    "eodm_peer_failed": (_i, [_p]),
+    "eodm_session_set_peer": (_i, [_p, _p]),
     "eodm_counts_partial": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_counts_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_loss_from_counts": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _p]),

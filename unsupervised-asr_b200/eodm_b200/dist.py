@@ -96,6 +96,62 @@ class Comm:
             self.handle = None
 
 
+class PeerGroup:
+    """The exchange fused with the loss over NVLink peer memory (csrc/peer.cu): one kernel per step publishes this
+    rank's partial counts, waits for the peers and forms global counts, loss and dloss/dS.  `allgather(bytes) ->
+    [bytes per rank]` ships the 64-byte CUDA IPC handles by any side channel."""
+
+    def __init__(self, handle, world, rank, K):
+        self.handle, self.world, self.rank, self.K = handle, world, rank, K
+
+    @classmethod
+    def bootstrap(cls, world, rank, K, allgather):
+        h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        check(lib.eodm_peer_create(world, rank, K, C.byref(h), buf))
+        handles = allgather(buf.raw)
+        assert len(handles) == world and all(len(x) == 64 for x in handles)
+        check(lib.eodm_peer_attach(h, C.create_string_buffer(b"".join(handles), 64 * world)))
+        return cls(h, world, rank, K)
+
+    @classmethod
+    def from_torch_distributed(cls, K):
+        import torch.distributed as td
+
+        world, rank = td.get_world_size(), td.get_rank()
+
+        def allgather(mine):
+            box = [None] * world
+            td.all_gather_object(box, mine)
+            return box
+
+        g = cls.bootstrap(world, rank, K, allgather)
+        td.barrier()          # every rank has mapped every buffer before the first step raises a flag
+        return g
+
+    def fused_loss(self, counts, py, need_grad=True, want_counts=False):
+        """counts: this rank's packed CUDA f32[K+1].  -> (loss f32[1], gS f32[K] or None, global counts or None)."""
+        import torch
+
+        K = self.K
+        loss = torch.empty(1, dtype=torch.float32, device=counts.device)
+        gS = torch.empty(K, dtype=torch.float32, device=counts.device) if need_grad else None
+        out = torch.empty(K + 1, dtype=torch.float32, device=counts.device) if want_counts else None
+        check(lib.eodm_peer_loss(self.handle, C.c_void_p(counts.data_ptr()), C.c_void_p(py.data_ptr()), 1e-15,
+                                 C.c_void_p(loss.data_ptr()), C.c_void_p(gS.data_ptr()) if need_grad else None,
+                                 C.c_void_p(out.data_ptr()) if want_counts else None,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return loss, gS, out
+
+    def failed(self):
+        return bool(lib.eodm_peer_failed(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib.eodm_peer_destroy(self.handle)
+            self.handle = None
+
+
 class GlooComm:
     """Same exchange through torch.distributed (any backend); used by the
     world_size-2 CPU tests of the sharding logic."""

@@ -63,6 +63,10 @@ class Session:
                                     self._loss.ctypes.data_as(C.c_void_p), dptr))
         return float(self._loss[0])
 
+    def set_peer(self, group):
+        """Use a dist.PeerGroup for the exchange of the following steps (None to undo)."""
+        check(lib.eodm_session_set_peer(self._h, group.handle if group is not None else None))
+
     def step_device(self, logits_ptr, mask_ptr, B, T, loss_ptr, dlogits_ptr, stream, comm=None):
         """Raw device-pointer step (ints): enqueue only."""
         check(lib.eodm_session_step_device(self._h, C.c_void_p(logits_ptr), C.c_void_p(mask_ptr), B, T,
