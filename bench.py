@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="timit_c2")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the partial counts meet -- one kernel over NVLink peer memory fused with the loss "
+                         "(csrc/peer.cu), or ncclAllReduce followed by the loss kernel; auto = peer from 4 GPUs up "
+                         "(measured: NCCL is 10 us ahead at N=2, the peer kernel 4 us ahead at N=8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -186,6 +190,10 @@ def main():
     frames = int(w["mask"].sum())
     table = E.NgramTable.from_ids(w["ids"], V, device=local)
     sess = E.Session(table, w["py"], B, T)
+    group = None
+    if world > 1 and (args.exchange == "peer" or (args.exchange == "auto" and world >= 4)):
+        group = E.dist.PeerGroup.from_torch_distributed(K)
+        sess.set_peer(group)
     logits_d = torch.tensor(w["logits"], device=dev)
     mask_d = torch.tensor(w["mask"], device=dev).to(torch.uint8)
     loss_d = torch.zeros(1, device=dev)
@@ -325,12 +333,19 @@ def main():
             "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
                        "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
+                       "exchange": None if world == 1 else
+                       ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
                        "path": "cuda-core trie walk (v2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }
         _emit(json.dumps(out))
     if world > 1:
+        if group is not None:
+            assert not group.failed(), "a peer never arrived at the exchange"
+            td.barrier()
+            sess.close()
+            group.close()
         comm.close()
         td.destroy_process_group()
 

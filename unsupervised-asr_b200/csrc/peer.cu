@@ -24,7 +24,8 @@
 #include "table.h"
 
 namespace {
-constexpr int kMaxPeers = 16;
+constexpr int kMaxPeers = 8;      // the GPUs of one NVSwitch node
+constexpr int kThreadsP = 512, kUnrollZ = 8;
 constexpr size_t kHdrBytes = 256;   // [0]: flag (u32), [64]: step counter (u32), [128]: error (i32)
 
 struct PeerView {
@@ -47,13 +48,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(1024) eodm_peer_loss_kernel(const __grid_constant__ PeerView pv,
-                                                              const float* __restrict__ counts,
-                                                              const float* __restrict__ py, float eps,
-                                                              float* __restrict__ loss, float* __restrict__ gS,
-                                                              float* __restrict__ counts_out) {
+__global__ void __launch_bounds__(kThreadsP) eodm_peer_loss_kernel(const __grid_constant__ PeerView pv,
+                                                                   const float* __restrict__ counts,
+                                                                   const float* __restrict__ py, float eps,
+                                                                   float* __restrict__ loss, float* __restrict__ gS,
+                                                                   float* __restrict__ counts_out) {
   __shared__ unsigned s_step;
   __shared__ int s_bad;
+  __shared__ float s_n;
   __shared__ float red[32];
   char* mine = pv.base[pv.rank];
   if (threadIdx.x == 0) {
@@ -65,10 +67,10 @@ __global__ void __launch_bounds__(1024) eodm_peer_loss_kernel(const __grid_const
   __syncthreads();
   const unsigned step = s_step;
   const int K = pv.K;
-  float* slot = reinterpret_cast<float*>(mine + kHdrBytes + (step & 1) * pv.slot_bytes);
-  for (int i = threadIdx.x; i <= K; i += blockDim.x) slot[i] = counts[i];
-  __threadfence_system();
-  __syncthreads();
+  const size_t slot_off = kHdrBytes + (step & 1) * pv.slot_bytes;
+  float* slot = reinterpret_cast<float*>(mine + slot_off);
+  for (int i = threadIdx.x; i <= K; i += kThreadsP) slot[i] = counts[i];
+  __syncthreads();   // the CTA's stores happen before thread 0's release, which is cumulative
   if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned*>(mine), step);
   if (threadIdx.x < pv.world) {
     const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
@@ -89,14 +91,33 @@ __global__ void __launch_bounds__(1024) eodm_peer_loss_kernel(const __grid_const
     }
     return;
   }
-  float n = 0.f;
-  for (int r = 0; r < pv.world; ++r)
-    n += __ldcv(reinterpret_cast<const float*>(pv.base[r] + kHdrBytes + (step & 1) * pv.slot_bytes) + K);
+  // global counts into the scratch plane: every rank's value of kUnrollZ entries is in flight at once (an NVLink
+  // round trip is ~1 us), then added in rank order -- identical bits on every rank
+  float* sum = reinterpret_cast<float*>(mine + kHdrBytes + 2 * pv.slot_bytes);
+  for (int base = 0; base <= K; base += kThreadsP * kUnrollZ) {
+    float v[kMaxPeers][kUnrollZ];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+#pragma unroll
+      for (int i = 0; i < kUnrollZ; ++i) {
+        const int z = base + threadIdx.x + kThreadsP * i;
+        v[r][i] = (r < pv.world && z <= K) ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
+      }
+#pragma unroll
+    for (int i = 0; i < kUnrollZ; ++i) {
+      const int z = base + threadIdx.x + kThreadsP * i;
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) t += v[r][i];   // absent ranks add +0
+      if (z <= K) sum[z] = t;
+      if (z == K) s_n = t;
+    }
+  }
+  __syncthreads();
+  const float n = s_n;
   float acc = 0.f;
-  for (int z = threadIdx.x; z < K; z += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < pv.world; ++r)   // rank order on every rank: identical bits everywhere
-      s += __ldcv(reinterpret_cast<const float*>(pv.base[r] + kHdrBytes + (step & 1) * pv.slot_bytes) + z);
+  for (int z = threadIdx.x; z < K; z += kThreadsP) {
+    const float s = sum[z];
     const float pz = s / n;
     const float p = py[z];
     acc += -p * logf(pz + eps);
@@ -108,7 +129,7 @@ __global__ void __launch_bounds__(1024) eodm_peer_loss_kernel(const __grid_const
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    float v = threadIdx.x < (kThreadsP >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
     if (threadIdx.x == 0) loss[0] = v;
   }
@@ -143,7 +164,7 @@ extern "C" int eodm_peer_create(int world, int rank, int K, eodm_peer** out, cha
   p->pv.rank = rank;
   p->pv.K = K;
   p->pv.slot_bytes = (((size_t)K + 1) * sizeof(float) + 255) & ~(size_t)255;
-  const size_t bytes = kHdrBytes + 2 * p->pv.slot_bytes;
+  const size_t bytes = kHdrBytes + 3 * p->pv.slot_bytes;   // two peer-visible slots + a private plane for the sums
   cudaError_t e = cudaGetDevice(&p->device);
   void* mem = nullptr;
   if (e == cudaSuccess) e = cudaMalloc(&mem, bytes);
@@ -206,7 +227,7 @@ extern "C" int eodm_peer_loss(eodm_peer* p, const float* counts, const float* py
                               float* counts_out, void* stream) {
   PEER_REQUIRE(p && counts && py && loss, EODM_EINVAL, "null pointer");
   PEER_REQUIRE(p->attached || p->pv.world == 1, EODM_EINVAL, "eodm_peer_attach has not been called");
-  eodm_peer_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->pv, counts, py, eps, loss, gS, counts_out);
+  eodm_peer_loss_kernel<<<1, kThreadsP, 0, (cudaStream_t)stream>>>(p->pv, counts, py, eps, loss, gS, counts_out);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_peer_loss_kernel launch failed: %s", cudaGetErrorString(e));
