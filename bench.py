@@ -192,8 +192,20 @@ def main():
     sess = E.Session(table, w["py"], B, T)
     group = None
     if world > 1 and (args.exchange == "peer" or (args.exchange == "auto" and world >= 4)):
-        group = E.dist.PeerGroup.from_torch_distributed(K)
-        sess.set_peer(group)
+        # CUDA IPC can be unavailable (container policy): every rank must agree before the first collective step
+        try:
+            group = E.dist.PeerGroup.from_torch_distributed(K)
+        except Exception as exc:                                        # noqa: BLE001
+            print("rank %d: peer exchange unavailable (%s)" % (rank, exc), file=sys.stderr)
+            group = None
+        ok = torch.tensor([1 if group is not None else 0], device=dev)
+        td.all_reduce(ok, op=td.ReduceOp.MIN)
+        if int(ok[0]) == 1:
+            sess.set_peer(group)
+        else:
+            if group is not None:
+                group.close()
+            group = None                                                # all ranks use ncclAllReduce
     logits_d = torch.tensor(w["logits"], device=dev)
     mask_d = torch.tensor(w["mask"], device=dev).to(torch.uint8)
     loss_d = torch.zeros(1, device=dev)
