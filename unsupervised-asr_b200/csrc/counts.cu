@@ -372,15 +372,17 @@ __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __
 struct BwdWalk {
   const uint2* ng;
   uint32_t cursor;
-  uint2 ahead;
+  uint2 ahead, ahead2;   // the next two stream entries: an L1 miss (a third of the reads) costs ~300 clk, one node ~220
   __device__ __forceinline__ void seek(uint32_t c) {
     cursor = c;
     ahead = __ldg(ng + c);
+    ahead2 = __ldg(ng + c + 1);
   }
   __device__ __forceinline__ uint2 next() {
     uint2 e = ahead;
     ++cursor;
-    ahead = __ldg(ng + cursor);
+    ahead = ahead2;
+    ahead2 = __ldg(ng + cursor + 1);  // every trie's stream is followed by slack words
     // the stream is read once, front to back: pull the next 128-byte line into L1 ahead of the walk
     // (the prefetch may run a few lines past this trie's slice; it stays inside the workspace)
     if ((cursor & 15u) == 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(ng + cursor + 32));
