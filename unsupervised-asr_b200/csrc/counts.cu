@@ -138,7 +138,7 @@ __device__ __forceinline__ float window_valid(const uint8_t* __restrict__ mask, 
 // ---------------------------------------------------------------------------
 struct FwdWalk {
   const uint32_t* nodes;
-  uint32_t cursor, ahead;
+  uint32_t cursor, ahead, ahead2;   // the next two stream entries (see BwdWalk)
   float* stage;     // this warp's [kStageLeaves][kStageLd] staging tile
   float* acc;       // per-CTA accumulators, leaf order
   uint32_t leaf0;   // leaf index of stage row 0
@@ -147,11 +147,13 @@ struct FwdWalk {
   __device__ __forceinline__ void seek(uint32_t c) {
     cursor = c;
     ahead = __ldg(nodes + c);
+    ahead2 = __ldg(nodes + c + 1);
   }
   __device__ __forceinline__ uint32_t next() {
     uint32_t e = ahead;
     ++cursor;
-    ahead = __ldg(nodes + cursor);  // every trie's stream is followed by one word of slack
+    ahead = ahead2;
+    ahead2 = __ldg(nodes + cursor + 1);  // every trie's stream is followed by slack words
     if ((cursor & 31u) == 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + cursor + 64));
     return e;
   }
