@@ -282,6 +282,22 @@ __global__ void __launch_bounds__(256) gather_softmax_fwd_vec_kernel(const float
   }
 }
 
+// plain softmax over rows (models/EODM.py:15) in the same 4-lane layout: NV independent 16-byte loads per thread
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __restrict__ x, int V, int64_t rows,
+                                                               float* __restrict__ y) {
+  const unsigned gm = group_mask();
+  const int gl = threadIdx.x & 3, V4 = V >> 2;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x / kG);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / kG) + (threadIdx.x >> 2); row < rows; row += stride) {
+    float4 r[NV];
+    load_row<NV>(r, x + row * V, V4, gl, -FLT_MAX);
+    float m, s;
+    softmax_row<NV>(r, gm, m, s);
+    store_row<NV>(y + row * V, r, V4, gl);
+  }
+}
+
 // One CTA per utterance: the slots are sorted by (frame, slot) in shared memory, so every frame finds the slots that
 // gathered it as one run without scanning all L slots.  Short runs (<= kShortRun slots) are summed by the frame's own
 // group in ascending slot order; a long run -- every padded slot gathers frame 0 (utils/tools.py:473-474,482-483), so
@@ -569,6 +585,16 @@ inline unsigned warp_rows_grid(int64_t rows) { return (unsigned)((rows + 7) / 8)
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
+
+// used by eodm_softmax_fwd_launch (ops.cu) for V % 4 == 0, V <= 128; false = not handled
+bool eodm_softmax_rows4_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st) {
+  const int sms = aux_sm_count();
+  if (!vec_ok(V) || sms <= 0 || ((((uintptr_t)logits | (uintptr_t)px) & 15) != 0)) return false;
+#define CALL(NV) softmax_rows_vec_kernel<NV><<<vec_grid(rows, sms), 256, 0, st>>>(logits, V, rows, px)
+  EODM_DISPATCH_NV(vec_nv(V), CALL);
+#undef CALL
+  return cudaGetLastError() == cudaSuccess;
+}
 
 extern "C" int eodm_gather_softmax_fwd(const float* logits, const int32_t* idx, int B, int T, int L, int V, float* px,
                                        void* stream) {

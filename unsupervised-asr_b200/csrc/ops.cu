@@ -227,6 +227,7 @@ static int vec_group(int V) {  // lanes per row for the vectorised softmax kerne
 
 int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st) {
   if (rows == 0) return EODM_OK;
+  if (eodm_softmax_rows4_launch(logits, rows, V, px, st)) return EODM_OK;   // rows in groups of 4 lanes x NV float4
   const int G = vec_group(V);
   if (G && (((uintptr_t)logits | (uintptr_t)px) & 15) == 0 && rows * G / 256 < 0x7fffffffLL) {
     EODM_SOFTMAX_DISPATCH(eodm_softmax_fwd_vec_kernel, G, logits, rows, V, px);
