@@ -121,7 +121,7 @@ run("REF x8 (asymptote: >> L2, >> launch latency)", 8000, 300, 70, 40)
 # the materialising op (API parity with P_Ngram.__call__): HBM-bound on its [B, T', K] output
 w = E.synth.workload("timit_ref")
 table = E.NgramTable.from_ids(w["ids"], w["V"], device=0)
-B, T, V, K, n = 64, 70, w["V"], table.K, w["n"]
+B, T, V, K, n = 512, 70, w["V"], table.K, w["n"]
 px = torch.softmax(torch.randn(B, T, V, device=dev), -1)
 p = torch.empty(B, T - n + 1, K, device=dev)
 ms = timed(lambda: check(lib.eodm_prob_fwd(table._h, P(px), B, T, P(p), st)))

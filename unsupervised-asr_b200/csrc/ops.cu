@@ -140,6 +140,35 @@ __global__ void __launch_bounds__(256) eodm_prob_fwd_kernel(const float* __restr
   }
 }
 
+// The same op in tiles: a CTA owns 256 consecutive n-grams (ids in registers, N compile-time) and 64 consecutive windows
+// of one utterance whose px rows (+ eps) sit in shared memory; every window's 256 outputs are one coalesced 1 KB
+// store.  HBM-bound on the [B, T', K] output, which is what this op exists to materialise.
+constexpr int kProbTW = 64;
+template <int N>
+__global__ void __launch_bounds__(256) eodm_prob_fwd_tile_kernel(const float* __restrict__ px,
+                                                                 const int32_t* __restrict__ ids, int V, int K, int T,
+                                                                 int Tp, int tiles_per_utt, float* __restrict__ p) {
+  extern __shared__ float rows[];   // [kProbTW + N - 1][V]
+  const int b = blockIdx.y / tiles_per_utt, t0 = (blockIdx.y % tiles_per_utt) * kProbTW;
+  const int nw = min(kProbTW, Tp - t0);
+  const float* src = px + ((int64_t)b * T + t0) * V;
+  for (int i = threadIdx.x; i < (nw + N - 1) * V; i += 256) rows[i] = __ldg(src + i) + kEps;
+  const int z = blockIdx.x * 256 + threadIdx.x;
+  int id[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) id[j] = z < K ? __ldg(ids + (int64_t)z * N + j) : -1;
+  __syncthreads();
+  if (z >= K) return;
+  float* out = p + ((int64_t)b * Tp + t0) * K + z;
+  for (int w = 0; w < nw; ++w) {
+    float q = 1.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (id[j] >= 0) q *= rows[(w + j) * V + id[j]];   // ids are a prefix followed by -1s: shorter n-grams stop early
+    out[(int64_t)w * K] = q;
+  }
+}
+
 // dpx[b][s][v] = sum_{(z,j): ids[z][j]==v, 0<=s-j<=T-n} dp[b][s-j][z] * prod_{j'!=j}(px[b][s-j+j'][ids[z][j']] + eps)
 // One thread per (row, v), gathering through the inverse index: deterministic, no atomics.
 __global__ void __launch_bounds__(256) eodm_prob_bwd_kernel(const float* __restrict__ px, const float* __restrict__ dp,
@@ -261,6 +290,20 @@ int eodm_prob_fwd_launch(const eodm_table* t, const float* px, int B, int T, flo
   if (W > 0x7fffffffLL) {
     eodm_set_error("B*(T-n+1) too large for the materialising op");
     return EODM_EUNSUPPORTED;
+  }
+  const int tiles = (Tp + kProbTW - 1) / kProbTW;
+  const size_t smem = (size_t)(kProbTW + t->n - 1) * t->V * sizeof(float);
+  if (t->n <= 8 && smem <= 48 * 1024 && (int64_t)B * tiles <= 65535) {
+    const dim3 grid((unsigned)((t->K + 255) / 256), (unsigned)(B * tiles));
+#define EODM_PROB_CASE(N) \
+  case N: eodm_prob_fwd_tile_kernel<N><<<grid, 256, smem, st>>>(px, t->d_ids, t->V, t->K, T, Tp, tiles, p); break;
+    switch (t->n) {
+      EODM_PROB_CASE(1) EODM_PROB_CASE(2) EODM_PROB_CASE(3) EODM_PROB_CASE(4)
+      EODM_PROB_CASE(5) EODM_PROB_CASE(6) EODM_PROB_CASE(7) EODM_PROB_CASE(8)
+    }
+#undef EODM_PROB_CASE
+    EODM_CHECK_LAUNCH("eodm_prob_fwd_tile_kernel");
+    return EODM_OK;
   }
   eodm_prob_fwd_kernel<<<(unsigned)W, 256, 0, st>>>(px, t->d_ids, t->n, t->V, t->K, T, Tp, p);
   EODM_CHECK_LAUNCH("eodm_prob_fwd_kernel");
