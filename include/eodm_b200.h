@@ -171,7 +171,7 @@ void eodm_peer_destroy(eodm_peer* p);
  * Collective, enqueue-only, CUDA-graph capturable (the step number lives on the device). */
 int eodm_peer_loss(eodm_peer* p, const float* counts, const float* py, float eps, float* loss, float* gS,
                    float* counts_out, void* stream);
-/* 1 if an earlier eodm_peer_loss gave up waiting (~2 s) for a peer and wrote NaN; synchronises the device. */
+/* 1 if an earlier eodm_peer_loss gave up waiting (~10 s) for a peer and wrote NaN; synchronises the device. */
 int eodm_peer_failed(eodm_peer* p);
 
 /* ---- one-call step with HOST buffers (what a plugin user times end to end) ---- */

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreadsP) eodm_peer_loss_kernel(const __grid_
     const long long t0 = clock64();
     // steps are compared as signed differences: the counter may wrap
     while ((int)(ld_acquire_sys(flag) - step) < 0) {
-      if (clock64() - t0 > (4LL << 30)) {   // ~2 s: a peer never arrived; report instead of hanging the GPU
+      if (clock64() - t0 > (20LL << 30)) {   // ~10 s: a peer never arrived; report instead of hanging the GPU
         s_bad = 1;
         break;
       }
