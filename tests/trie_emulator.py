@@ -15,7 +15,7 @@ def _phone(e):
 
 
 def _nchild(e):
-    return (int(e) >> 16) & 0x7FFF
+    return (int(e) >> 16) & 0x3FFF          # bit 30 is the flat-tail mark (table.h EODM_NODE_CHAIN)
 
 
 def _hasz(e):

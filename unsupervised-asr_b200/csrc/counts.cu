@@ -231,6 +231,25 @@ __device__ __forceinline__ void fwd_visit(FwdWalk& w, const TrieArg& tr, const f
       w.emit(s);
     }
     if constexpr (L + 1 < DEPTH) {
+      if (EODM_NODE_CHAIN(e)) {
+        // flat tail: one node per remaining level, the n-gram ends at the last one -- straight-line code
+        constexpr int M = DEPTH - 1 - L;
+        uint32_t d[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) d[i] = w.next();
+#pragma unroll
+        for (int i = 0; i + 1 < M; ++i) {
+          const float* rw = Pl + EODM_NODE_PHONE(d[i]) * ld + tr.off[L + 1 + i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) q[r] *= rw[32 * r];
+        }
+        const float* rw = Pl + EODM_NODE_PHONE(d[M - 1]) * ld + tr.off[DEPTH - 1];
+        float s = q[0] * rw[0];   // the same association as the deepest level's own loop
+#pragma unroll
+        for (int r = 1; r < R; ++r) s = fmaf(q[r], rw[32 * r], s);
+        w.emit(s);
+        continue;
+      }
       const int nc = EODM_NODE_NCHILD(e);
       if (nc) fwd_visit<L + 1, DEPTH, R>(w, tr, Pl, ld, q, nc);
     }
@@ -443,6 +462,31 @@ __device__ __forceinline__ void bwd_visit(BwdWalk& w, const int (&off)[EODM_MAX_
       const uint2 e = w.next();
       const float g = __uint_as_float(e.y);  // 0 unless an n-gram ends here
       const float* row = Pl + EODM_NODE_PHONE(e.x) * ld + off[L];
+      if (EODM_NODE_CHAIN(e.x)) {
+        // flat tail: one node per remaining level -- Horner from the deepest node up, straight-line code, the same
+        // operations in the same order as the level-by-level walk
+        constexpr int M = DEPTH - 1 - L;
+        uint2 d[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) d[i] = w.next();
+        float t[R];
+        {
+          const float* rw = Pl + EODM_NODE_PHONE(d[M - 1].x) * ld + off[DEPTH - 1];
+          const float gl = __uint_as_float(d[M - 1].y), gp = M >= 2 ? __uint_as_float(d[M >= 2 ? M - 2 : 0].y) : g;
+#pragma unroll
+          for (int r = 0; r < R; ++r) t[r] = fmaf(rw[32 * r], gl, gp);
+        }
+#pragma unroll
+        for (int i = M - 2; i >= 0; --i) {
+          const float* rw = Pl + EODM_NODE_PHONE(d[i].x) * ld + off[L + 1 + i];
+          const float gp = i >= 1 ? __uint_as_float(d[i >= 1 ? i - 1 : 0].y) : g;
+#pragma unroll
+          for (int r = 0; r < R; ++r) t[r] = fmaf(rw[32 * r], t[r], gp);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = fmaf(row[32 * r], t[r], kFirst ? init : out[r]);
+        return;
+      }
       const int nc = EODM_NODE_NCHILD(e.x);
       if (nc) {
         float s[R];

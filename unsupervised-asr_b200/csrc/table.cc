@@ -67,7 +67,7 @@ struct TrieBuilder {
     return c;
   }
   void push_node(uint32_t phone, int nchild, bool hasz) {
-    if (nchild > 0x7fff) overflow = true;
+    if (nchild > 0x3fff) overflow = true;
     nodes.push_back(phone | (uint32_t(nchild) << 16) | (uint32_t(hasz) << 31));
   }
   // emits the first node of group [i, e) at level d and its whole subtree;
@@ -136,6 +136,23 @@ struct TrieBuilder {
       acc += c;
     }
     total_cost = acc;
+  }
+  // Marks the nodes whose subtree is a single path to level `full_depth - 1` (levels count from 0 at the root; the
+  // stream starts at level 1) with no n-gram ending before the path's last node: EODM_NODE_CHAIN.
+  void mark_chains(int full_depth) {
+    size_t i = 0;
+    while (i < nodes.size()) i = mark_from(i, 1, full_depth);
+  }
+  size_t mark_from(size_t i, int level, int full_depth) {
+    const int nc = (int)EODM_NODE_NCHILD(nodes[i]);
+    size_t j = i + 1;
+    for (int c = 0; c < nc; ++c) j = mark_from(j, level + 1, full_depth);
+    if (nc == 1) {
+      const uint32_t ch = nodes[i + 1];
+      const bool leaf_at_bottom = level + 1 == full_depth - 1 && EODM_NODE_NCHILD(ch) == 0 && EODM_NODE_HASZ(ch);
+      if (leaf_at_bottom || (!EODM_NODE_HASZ(ch) && EODM_NODE_CHAIN(ch))) nodes[i] |= 1u << 30;
+    }
+    return j;
   }
   uint32_t total_cost = 0;
 };
@@ -270,8 +287,9 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
     });
     TrieBuilder tb(keys);
     tb.build();
+    if (n <= 5 || n == 8) tb.mark_chains(n);   // kernel sizes whose walk is compiled with exactly n levels
     if (tb.overflow) {
-      eodm_set_error("a trie node has more than 32767 children (trie %d)", j);
+      eodm_set_error("a trie node has more than 16383 children (trie %d)", j);
       rc = EODM_EUNSUPPORTED;
       break;
     }

@@ -26,7 +26,10 @@
 #define EODM_MAX_N 8
 
 #define EODM_NODE_PHONE(e) ((e) & 0xffffu)
-#define EODM_NODE_NCHILD(e) (((e) >> 16) & 0x7fffu)
+#define EODM_NODE_NCHILD(e) (((e) >> 16) & 0x3fffu)
+// bit 30: everything below this node is ONE path down to the deepest level of the trie (one child per node, an n-gram
+// ends only at its last node) -- the walks take such tails as straight-line code instead of one loop per level
+#define EODM_NODE_CHAIN(e) (((e) >> 30) & 1u)
 #define EODM_NODE_HASZ(e) ((e) >> 31)
 
 #define EODM_UNIT_SELF 1u   // the n-gram ends at the root itself (order-1 n-gram in trie 0)
