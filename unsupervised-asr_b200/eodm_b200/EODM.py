@@ -396,9 +396,12 @@ class _DenseBigramLossFn(torch.autograd.Function):
         counts = torch.empty(table.K + 1, dtype=torch.float32, device=px.device)
         check(lib.eodm_bigram_gather(table._h, _ptr(Cm), _ptr(counts), _stream()))
         counts[table.K:] = N
-        if comm is not None:
-            comm.allreduce_counts(counts, table.K)                 # K+1 floats, not V*V
-        loss, gS = loss_from_counts(counts, py, table.K, True)
+        if comm is not None and hasattr(comm, "fused_loss"):       # exchange fused with the loss (dist.PeerGroup)
+            loss, gS, _ = comm.fused_loss(counts, py, True)
+        else:
+            if comm is not None:
+                comm.allreduce_counts(counts, table.K)             # K+1 floats, not V*V
+            loss, gS = loss_from_counts(counts, py, table.K, True)
         ctx.table, ctx.mask = table, mask
         ctx.save_for_backward(px, gS)
         return loss.reshape(())
