@@ -70,8 +70,11 @@ __global__ void __launch_bounds__(kThreadsP) eodm_peer_loss_kernel(const __grid_
   const size_t slot_off = kHdrBytes + (step & 1) * pv.slot_bytes;
   float* slot = reinterpret_cast<float*>(mine + slot_off);
   for (int i = threadIdx.x; i <= K; i += kThreadsP) slot[i] = counts[i];
-  __syncthreads();   // the CTA's stores happen before thread 0's release, which is cumulative
-  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned*>(mine), step);
+  __syncthreads();   // the CTA's stores happen before thread 0's fence + release (the pattern of a grid-wide barrier)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned*>(mine), step);
+  }
   if (threadIdx.x < pv.world) {
     const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
     const long long t0 = clock64();
