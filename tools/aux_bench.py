@@ -1,7 +1,7 @@
 """HBM roofline of the kernels either side of the counts walk (the softmax pair and the
 materialising P_Ngram op): CUDA events around one C-ABI call, L2 flushed between calls (256 MiB write), buffers
 preallocated, median of 9.  Prints a markdown table (copied into profiles/ by hand) and a CPU figure for the same op
-on a bounded sample through the oracle (test infrastructure, used here as the baseline beside the GPU number)."""
+on a bounded sample: plain torch-CPU statements of the reference's lines, written out below (all host threads)."""
 import ctypes as C
 import json
 import os
@@ -16,7 +16,52 @@ import torch
 
 import eodm_b200 as E
 from eodm_b200._lib import check, lib
-from oracle import eodm_oracle as O
+
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+class O:
+    """torch-CPU statements of the reference lines, for the CPU column only (no parity claim rests on them)."""
+
+    @staticmethod
+    def softmax(lg):                                            # models/EODM.py:15
+        return torch.softmax(torch.from_numpy(lg), -1)
+
+    @staticmethod
+    def gather_softmax(lg, idx):                                # main_EODM.py:163 + models/EODM.py:15
+        t = torch.from_numpy(lg)
+        ix = torch.from_numpy(idx.astype(np.int64))[:, :, None].expand(-1, -1, t.shape[2])
+        return torch.softmax(torch.gather(t, 1, ix), -1)
+
+    @staticmethod
+    def ce_loss(lg, labels, V, confidence):                     # utils/tools.py:538-557, forward + autograd
+        x = torch.from_numpy(lg).clone().requires_grad_(True)
+        lab = torch.from_numpy(labels.astype(np.int64))
+        low = (1.0 - confidence) / (V - 1)
+        soft = torch.full(x.shape, low)
+        soft.scatter_(2, lab[:, :, None], confidence)
+        xent = -(soft * torch.log_softmax(x, -1)).sum(-1)
+        norm = -(confidence * np.log(confidence) + (V - 1) * low * np.log(low + 1e-20))
+        mk = (lab > 0).float()
+        loss = ((xent - norm) * mk).sum() / mk.sum()
+        loss.backward()
+        return loss
+
+    @staticmethod
+    def frames_constrain_loss(lg, align):                       # utils/tools.py:419-434, forward + autograd
+        x = torch.from_numpy(lg).clone().requires_grad_(True)
+        B, T, V = x.shape
+        al = align.astype(np.int64) + 1
+        end = al.max(1)
+        gate = np.zeros((B, T), dtype=np.float32)
+        for b in range(B):
+            gate[b, 2:min(T, end[b])] = 1.0
+            gate[b, al[b][(al[b] >= 0) & (al[b] < T)]] = 0.0
+        p = torch.softmax(x, -1)
+        d = ((p[:, :-1] - p[:, 1:]) ** 2).mean(-1)
+        loss = (d * torch.from_numpy(gate[:, 1:])).sum()
+        loss.backward()
+        return loss
 
 dev = torch.device("cuda:0")
 PEAK = 6555.2
@@ -127,6 +172,6 @@ p = torch.empty(B, T - n + 1, K, device=dev)
 ms = timed(lambda: check(lib.eodm_prob_fwd(table._h, P(px), B, T, P(p), st)))
 report("P_Ngram.__call__ (materialising)", "B=%d T=%d V=%d n=%d K=%d" % (B, T, V, n, K), 4.0 * p.numel() + 4.0 * px.numel(), ms)
 
-print("| kernel | shape | algorithmic MB | ms | GB/s | of %.0f GB/s | CPU (oracle, numpy/torch) |" % PEAK)
+print("| kernel | shape | algorithmic MB | ms | GB/s | of %.0f GB/s | CPU (torch, all host threads) |" % PEAK)
 print("|---|---|---|---|---|---|---|")
 print("\n".join(rows_out))
