@@ -50,7 +50,7 @@ struct Mat {
 
 // operand stored [K][MN] if mn-major else [MN][K]
 template <bool A_MN, bool B_MN>
-double run(int M, int N, int K, bool check, int reps, const char* name, bool two = false) {
+double run(int M, int N, int K, bool check, int reps, const char* name, bool two = false, int split_from = -1) {
   Mat A, B;
   if (A_MN) A.init(K, M, 1u); else A.init(M, K, 1u);
   if (B_MN) B.init(K, N, 2u); else B.init(N, K, 2u);
@@ -69,6 +69,13 @@ double run(int M, int N, int K, bool check, int reps, const char* name, bool two
   Args a;
   a.M = M; a.N = N; a.K = K; a.scale_out = check ? so : nullptr; a.C = C; a.ldc = N; a.c_row_shift = check ? 1 : 0;
   a.accumulate = 0; a.m_tiles = two ? (M + 255) / 256 : (M + kTM - 1) / kTM; a.n_tiles = (N + kTN - 1) / kTN;
+  float* C2 = nullptr;
+  a.split_from = a.m_tiles * a.n_tiles; a.C2 = nullptr;
+  if (two && split_from >= 0) {
+    CK(cudaMalloc(&C2, (size_t)(M + 1) * N * 4));
+    CK(cudaMemset(C2, 0, (size_t)(M + 1) * N * 4));
+    a.split_from = split_from; a.C2 = C2;
+  }
   auto go = [&]() { return two ? launch2<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0) : launch<A_MN, B_MN>(ta, tal, tb, tbl, a, sms, 0); };
   CK(go());
   CK(cudaDeviceSynchronize());
@@ -81,6 +88,11 @@ double run(int M, int N, int K, bool check, int reps, const char* name, bool two
     CK(cudaMemcpy(ha.data(), A.x, ha.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hb.data(), B.x, hb.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hc.data(), C, hc.size() * 4, cudaMemcpyDeviceToHost));
+    if (C2) {   // the second halves of the split tiles
+      std::vector<float> h2(hc.size());
+      CK(cudaMemcpy(h2.data(), C2, h2.size() * 4, cudaMemcpyDeviceToHost));
+      for (size_t q = 0; q < hc.size(); ++q) hc[q] += h2[q];
+    }
     CK(cudaMemcpy(hs.data(), so, hs.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0;
     int bad_i = -1, bad_j = -1;
@@ -115,6 +127,7 @@ double run(int M, int N, int K, bool check, int reps, const char* name, bool two
     result = ms;
   }
   A.free_(); B.free_(); cudaFree(C); cudaFree(so);
+  if (C2) cudaFree(C2);
   return result;
 }
 
@@ -137,10 +150,13 @@ int main(int argc, char** argv) {
     w2 = fmax(w2, run<false, true>(300, 640, 200, true, 0, "2-CTA K/MN", true));
     w2 = fmax(w2, run<true, true>(288, 640, 200, true, 0, "2-CTA MN/MN", true));
     w2 = fmax(w2, run<true, true>(20 * 128, 8 * 256, 1000, true, 0, "2-CTA MN/MN 80 tiles", true));
+    w2 = fmax(w2, run<true, true>(20 * 128, 8 * 256, 1000, true, 0, "2-CTA MN/MN, tiles 74.. split", true, 74));
+    w2 = fmax(w2, run<false, true>(300, 640, 200, true, 0, "2-CTA K/MN, every tile split", true, 0));
     printf("2-CTA worst %.3e -> %s\n", w2, w2 < 5e-6 ? "OK" : "FAIL");
     worst = fmax(worst, w2);
     if (timing && w2 < 5e-6) {
       run<true, true>(5120, 5120, 32768, false, 3, "2-CTA fwd  (MN/MN)", true);
+      run<true, true>(5120, 5120, 32768, false, 3, "2-CTA fwd, last wave split", true, 370);
       run<false, false>(32768, 5120, 5120, false, 3, "2-CTA bwd1 (K/K)", true);
       run<false, true>(32768, 5120, 5120, false, 3, "2-CTA bwd2 (K/MN)", true);
     }

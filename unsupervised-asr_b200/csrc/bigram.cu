@@ -80,6 +80,21 @@ __global__ void __launch_bounds__(256) eodm_bigram_split_px_kernel(const float4*
     Xalo[i] = make_float4(w * l[0], w * l[1], w * l[2], w * l[3]);
   }
 }
+// C += C2 over the 256 x 256 tiles [tile0, tile0 + gridDim.x) (tile order of the pair kernel: row-major over n_tiles):
+// the two halves of a reduction cut in two are added in a fixed order
+__global__ void __launch_bounds__(256) eodm_bigram_add_tiles_kernel(float* __restrict__ C, const float* __restrict__ C2,
+                                                                    int V, int n_tiles, int tile0) {
+  const int tile = tile0 + blockIdx.x, m0 = (tile / n_tiles) * 256, n0 = (tile % n_tiles) * 256;
+  for (int e = threadIdx.x; e < 256 * 64; e += 256) {
+    const int i = m0 + e / 64, j = n0 + (e % 64) * 4;
+    if (i < V && j < V) {   // V is a multiple of 128: a float4 never straddles the edge
+      float4 a = *reinterpret_cast<float4*>(C + (size_t)i * V + j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(C2 + (size_t)i * V + j));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      *reinterpret_cast<float4*>(C + (size_t)i * V + j) = a;
+    }
+  }
+}
 __global__ void __launch_bounds__(256) eodm_bigram_split_lo_kernel(const float4* __restrict__ x, long long n4,
                                                                    float4* __restrict__ lo) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -210,8 +225,24 @@ extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B
   a.scale_out = nullptr;
   a.C = C; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
   a.m_tiles = (V + 255) / 256; a.n_tiles = (V + 255) / 256;   // 256 x 256 tiles, one per CTA pair
-  const cudaError_t e = eodm_tma::launch2<true, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st);
-  return e == cudaSuccess ? EODM_OK : fail_launch("gemm3x_tma2_kernel", e);
+  // Tiles rarely divide over the CTA pairs (V=5120: 400 tiles over 74 pairs = 5.4 waves).  When the last wave is at
+  // most half full its tiles are cut in two along the reduction: it then takes half a tile's time.  The second halves
+  // land in the (forward-unused) G_lo plane and are added afterwards, in a fixed order.
+  const int tiles = a.m_tiles * a.n_tiles, pairs = sms / 2;
+  const int rest = pairs > 0 ? tiles % pairs : 0;
+  a.split_from = tiles;
+  a.C2 = nullptr;
+  if (tiles > pairs && rest > 0 && 2 * rest <= pairs && NR >= 4096 && (((uintptr_t)C) & 15) == 0) {
+    a.split_from = tiles - rest;
+    a.C2 = w.Glo;
+  }
+  cudaError_t e = eodm_tma::launch2<true, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st);
+  if (e != cudaSuccess) return fail_launch("gemm3x_tma2_kernel", e);
+  if (a.split_from < tiles) {
+    eodm_bigram_add_tiles_kernel<<<tiles - a.split_from, 256, 0, st>>>(C, w.Glo, V, a.n_tiles, a.split_from);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_add_tiles_kernel", e);
+  }
+  return EODM_OK;
 }
 
 extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B, int T, int V, const float* G,
@@ -248,6 +279,7 @@ extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B
   a.scale_out = w.wv;
   a.C = dpx; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
   a.m_tiles = (int)((NR + 255) / 256); a.n_tiles = (V + 255) / 256;
+  a.split_from = a.m_tiles * a.n_tiles; a.C2 = nullptr;   // 2560 tiles at config 4: 34.6 waves, nothing to gain
   if ((e = eodm_tma::launch2<false, false>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
     return fail_launch("gemm3x_tma2_kernel", e);
   // position 1:  dpx[r+1][v] += sum_u Xa[r][u] G[u][v]               (wv is folded into Xa)
@@ -256,6 +288,7 @@ extern "C" int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B
   a.M = (int)NR - 1; a.scale_out = nullptr;
   a.c_row_shift = 1; a.accumulate = 1;
   a.m_tiles = (int)((NR - 1 + 255) / 256);
+  a.split_from = a.m_tiles * a.n_tiles;
   if ((e = eodm_tma::launch2<false, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
     return fail_launch("gemm3x_tma2_kernel", e);
   return EODM_OK;

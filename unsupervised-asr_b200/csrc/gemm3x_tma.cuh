@@ -47,7 +47,31 @@ struct Args {
   long long ldc, c_row_shift;
   int accumulate;           // 0: C = ..., 1: C += ...
   int m_tiles, n_tiles;
+  // pair kernel only: tiles [split_from, m_tiles * n_tiles) are cut in two along the reduction so that the last,
+  // partly filled wave of tiles takes half a tile's time; the second halves land in C2 (same geometry as C, added to
+  // C by the caller afterwards).  split_from = m_tiles * n_tiles (or C2 = nullptr) switches it off.
+  int split_from;
+  float* C2;
 };
+
+// task -> (tile, first chunk, number of chunks, output plane) for the pair kernel
+struct Task2 {
+  int tile, c0, nc, second;
+};
+__device__ __forceinline__ Task2 task2_of(const Args& a, int task, int chunks) {
+  Task2 t;
+  const int tiles = a.m_tiles * a.n_tiles;
+  if (task < a.split_from || a.split_from >= tiles) {
+    t.tile = task; t.c0 = 0; t.nc = chunks; t.second = 0;
+  } else {
+    const int h = task - a.split_from, half = (chunks + 1) / 2;
+    t.tile = a.split_from + (h >> 1);
+    t.second = h & 1;
+    t.c0 = t.second ? half : 0;
+    t.nc = t.second ? chunks - half : half;
+  }
+  return t;
+}
 
 struct Bars {
   uint64_t full[kStages], empty[kStages], d_full[2], d_empty[2];
@@ -322,10 +346,10 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_tasks = a.m_tiles * a.n_tiles;
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int n_tasks = tiles + (a.split_from < tiles ? tiles - a.split_from : 0);
   const int chunks = (a.K + kBK - 1) / kBK;
   const int my_tasks = (n_tasks - pair + n_pairs - 1) / n_pairs;
-  const int rounds_per_task = (chunks + kRoundChunks - 1) / kRoundChunks;
 
   if (warp == 1) tmem_alloc2(&tmem_slot, 512);
   if (tid == 0) {
@@ -349,14 +373,14 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
     if (lane == 0) {
       int it = 0;
       for (int t = 0; t < my_tasks; ++t) {
-        const int task = pair + t * n_pairs;
-        const int m0 = (task / a.n_tiles) * 256 + (int)rank * 128, n0 = (task % a.n_tiles) * 256 + (int)rank * 128;
-        for (int c = 0; c < chunks; ++c, ++it) {
+        const Task2 tk = task2_of(a, pair + t * n_pairs, chunks);
+        const int m0 = (tk.tile / a.n_tiles) * 256 + (int)rank * 128, n0 = (tk.tile % a.n_tiles) * 256 + (int)rank * 128;
+        for (int c = 0; c < tk.nc; ++c, ++it) {
           const int s = it % kStages2, use = it / kStages2;
           if (use > 0) mbar_wait(&bars.empty[s], (uint32_t)((use - 1) & 1));
           if (rank == 0) mbar_expect_tx(&bars.full[s], 2 * kStageBytes2);
           const uint32_t base = stages + (uint32_t)s * kStageBytes2;
-          const int k0 = c * kBK;
+          const int k0 = (tk.c0 + c) * kBK;
           load_operand2<A_MN>(base, &ta, m0, k0, &bars.full[s]);
           load_operand2<B_MN>(base + 2 * kHalfBytes, &tb, n0, k0, &bars.full[s]);
           load_operand2<A_MN>(base + kHalfBytes, &ta_lo, m0, k0, &bars.full[s]);
@@ -371,7 +395,8 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
                              ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int it = 0, round = 0;
       for (int t = 0; t < my_tasks; ++t) {
-        for (int c = 0; c < chunks; ++c, ++it) {
+        const int nc = task2_of(a, pair + t * n_pairs, chunks).nc;
+        for (int c = 0; c < nc; ++c, ++it) {
           const int bank = round & 1;
           const bool first = (c % kRoundChunks) == 0;
           if (first && round >= 2) mbar_wait(&bars.d_empty[bank], (uint32_t)(((round >> 1) - 1) & 1));
@@ -390,7 +415,7 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
             mma2_tf32_ss(d, ah, bl, idesc, 1u);
           }
           mma2_commit_both(&bars.empty[s]);
-          if ((c % kRoundChunks) == kRoundChunks - 1 || c == chunks - 1) {
+          if ((c % kRoundChunks) == kRoundChunks - 1 || c == nc - 1) {
             mma2_commit_both(&bars.d_full[bank]);
             ++round;
           }
@@ -406,6 +431,8 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
     for (int k = 0; k < 128; ++k) acc[k] = 0.f;
     int round = 0;
     for (int t = 0; t < my_tasks; ++t) {
+      const Task2 tk = task2_of(a, pair + t * n_pairs, chunks);
+      const int rounds_per_task = (tk.nc + kRoundChunks - 1) / kRoundChunks;
       for (int r = 0; r < rounds_per_task; ++r, ++round) {
         const int bank = round & 1;
         mbar_wait(&bars.d_full[bank], (uint32_t)((round >> 1) & 1));
@@ -425,12 +452,11 @@ gemm3x_tma2_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&bars.d_empty[bank], 0);
       }
-      const int task = pair + t * n_pairs;
-      const int m0 = (task / a.n_tiles) * 256 + (int)rank * 128, n0 = (task % a.n_tiles) * 256;
+      const int m0 = (tk.tile / a.n_tiles) * 256 + (int)rank * 128, n0 = (tk.tile % a.n_tiles) * 256;
       const int i = m0 + quarter * 32 + lane;
       if (i < a.M) {
         const float so = a.scale_out ? __ldg(a.scale_out + i) : 1.f;
-        float* out = a.C + (i + a.c_row_shift) * a.ldc + n0 + half * 128;
+        float* out = (tk.second ? a.C2 : a.C) + (i + a.c_row_shift) * a.ldc + n0 + half * 128;
         const int jn = a.N - (n0 + half * 128);
         if (jn >= 128 && (((uintptr_t)out) & 15) == 0) {
 #pragma unroll
@@ -517,7 +543,8 @@ inline cudaError_t launch2(const CUtensorMap& ta, const CUtensorMap& ta_lo, cons
   auto k = gemm3x_tma2_kernel<A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2);
   if (e != cudaSuccess) return e;
-  const int tasks = a.m_tiles * a.n_tiles;   // 256 x 256 tiles, one per CTA pair
+  const int tiles = a.m_tiles * a.n_tiles;   // 256 x 256 tiles, one per CTA pair
+  const int tasks = tiles + (a.split_from < tiles ? tiles - a.split_from : 0);
   const int pairs = tasks < sm_count / 2 ? tasks : sm_count / 2;
   k<<<2 * pairs, kThreads, kSmemBytes2, st>>>(ta, ta_lo, tb, tb_lo, a);
   return cudaGetLastError();
