@@ -246,6 +246,7 @@ def test_trie_walk_emulation_matches_oracle(eodm, seed, V, n, K, B, T, mixed, du
     d_ref = O.counts_bwd(px, mask, ids, n, gS)
     d = E.emulate_bwd(t, px, mask, gS)
     assert np.abs(d - d_ref).max() <= 1e-12 * max(1e-300, np.abs(d_ref).max())
+    E.check_chain_marks(t)                                      # the flat-tail marks against their definition
 
 
 def test_trie_sizes_timit(eodm, golden):
@@ -253,6 +254,7 @@ def test_trie_sizes_timit(eodm, golden):
     t = eodm.NgramTable.from_ids(golden["timit1000_ids"], 40, device=-1)
     tr = t.debug_trie(0)
     assert len(tr["units"]) == 242 and len(tr["perm"]) == 1000
+    assert E.check_chain_marks(t) > 1000                        # flat tails: most 5-grams end in a single path
     assert len(tr["nodes"]) == 242 + 518 + 779 + 1000
     assert sorted(tr["perm"].tolist()) == list(range(1000))
 

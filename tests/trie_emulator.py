@@ -22,6 +22,42 @@ def _hasz(e):
     return int(e) >> 31
 
 
+def _chain(e):
+    return (int(e) >> 30) & 1
+
+
+def check_chain_marks(table):
+    """The flat-tail bit (table.h EODM_NODE_CHAIN) of every node of every trie against its definition: set iff the
+    node has one child and everything below is a single path that reaches the deepest level (n - 1), with an n-gram
+    ending at the path's last node and nowhere before.  Returns the number of marked nodes."""
+    n = table.n
+    marked = 0
+    for j in range(n):
+        nodes = table.debug_trie(j)["nodes"]
+
+        def parse(i, level):
+            """-> (next index, is the subtree of node i a pure path to level n-1 that starts at i)."""
+            nc = _nchild(nodes[i])
+            k = i + 1
+            child_pure = []
+            for _ in range(nc):
+                k, pure = parse(k, level + 1)
+                child_pure.append(pure)
+            if nc == 0:
+                pure_here = level == n - 1 and bool(_hasz(nodes[i]))
+            else:
+                pure_here = nc == 1 and child_pure[0] and not _hasz(nodes[i])
+            want = 1 if (nc == 1 and child_pure[0] and (n <= 5 or n == 8)) else 0
+            assert _chain(nodes[i]) == want, (j, i, level, nc, _chain(nodes[i]), want)
+            return k, pure_here
+
+        i = 0
+        while i < len(nodes):
+            i, _ = parse(i, 1)
+        marked += sum(_chain(e) for e in nodes)
+    return marked
+
+
 def _ranges(units, total_cost):
     cost_before = units[:, 3].astype(np.int64)
     n = len(units)
