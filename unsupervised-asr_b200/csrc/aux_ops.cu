@@ -298,6 +298,82 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __re
   }
 }
 
+// Wide rows (128 < V <= 8192, the character inventories of the dense bigram path): one CTA of 256 threads per row, the
+// row in registers (NV float4 per thread), one read and one write per element
+__device__ __forceinline__ float block_max_256(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r += red[w];
+  __syncthreads();
+  return r;
+}
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_wide_kernel(const float* __restrict__ x, int V, float* __restrict__ y) {
+  __shared__ float red[8];
+  const int V4 = V >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + (int64_t)blockIdx.x * V);
+  float4 r[NV];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = threadIdx.x + 256 * k;
+    r[k] = c < V4 ? __ldg(src + c) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    m = fmaxf(m, fmaxf(fmaxf(r[k].x, r[k].y), fmaxf(r[k].z, r[k].w)));
+  }
+  m = block_max_256(m, red);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    r[k] = make_float4(expf(r[k].x - m), expf(r[k].y - m), expf(r[k].z - m), expf(r[k].w - m));
+    s += (r[k].x + r[k].y) + (r[k].z + r[k].w);
+  }
+  s = block_sum_256(s, red);
+  const float inv = 1.0f / s;
+  float4* dst = reinterpret_cast<float4*>(y + (int64_t)blockIdx.x * V);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = threadIdx.x + 256 * k;
+    if (c < V4) dst[c] = make_float4(r[k].x * inv, r[k].y * inv, r[k].z * inv, r[k].w * inv);
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_vjp_wide_kernel(const float* __restrict__ px, const float* __restrict__ dpx,
+                                                               int V, float* __restrict__ dx) {
+  __shared__ float red[8];
+  const int V4 = V >> 2;
+  const float4* ps = reinterpret_cast<const float4*>(px + (int64_t)blockIdx.x * V);
+  const float4* ds = reinterpret_cast<const float4*>(dpx + (int64_t)blockIdx.x * V);
+  float4 p[NV], d[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = threadIdx.x + 256 * k;
+    p[k] = c < V4 ? __ldg(ps + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    d[k] = c < V4 ? __ldg(ds + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s = fmaf(p[k].x, d[k].x, fmaf(p[k].y, d[k].y, fmaf(p[k].z, d[k].z, fmaf(p[k].w, d[k].w, s))));
+  }
+  s = block_sum_256(s, red);
+  float4* dst = reinterpret_cast<float4*>(dx + (int64_t)blockIdx.x * V);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = threadIdx.x + 256 * k;
+    if (c < V4) dst[c] = make_float4(p[k].x * (d[k].x - s), p[k].y * (d[k].y - s), p[k].z * (d[k].z - s), p[k].w * (d[k].w - s));
+  }
+}
+
 // One CTA per utterance: the slots are sorted by (frame, slot) in shared memory, so every frame finds the slots that
 // gathered it as one run without scanning all L slots.  Short runs (<= kShortRun slots) are summed by the frame's own
 // group in ascending slot order; a long run -- every padded slot gathers frame 0 (utils/tools.py:473-474,482-483), so
@@ -589,10 +665,27 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 // used by eodm_softmax_fwd_launch (ops.cu) for V % 4 == 0, V <= 128; false = not handled
 bool eodm_softmax_rows4_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st) {
   const int sms = aux_sm_count();
-  if (!vec_ok(V) || sms <= 0 || ((((uintptr_t)logits | (uintptr_t)px) & 15) != 0)) return false;
+  if ((V & 3) != 0 || sms <= 0 || ((((uintptr_t)logits | (uintptr_t)px) & 15) != 0)) return false;
+  if (V > 128) {   // wide rows: one CTA per row
+    if (V > 8192 || rows > 0x7fffffffLL) return false;
+#define CALLW(NV) softmax_wide_kernel<NV><<<(unsigned)rows, 256, 0, st>>>(logits, V, px)
+    EODM_DISPATCH_NV((V / 4 + 255) / 256, CALLW);
+#undef CALLW
+    return cudaGetLastError() == cudaSuccess;
+  }
 #define CALL(NV) softmax_rows_vec_kernel<NV><<<vec_grid(rows, sms), 256, 0, st>>>(logits, V, rows, px)
   EODM_DISPATCH_NV(vec_nv(V), CALL);
 #undef CALL
+  return cudaGetLastError() == cudaSuccess;
+}
+
+bool eodm_softmax_vjp_wide_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st) {
+  if ((V & 3) != 0 || V <= 128 || V > 8192 || rows > 0x7fffffffLL ||
+      ((((uintptr_t)px | (uintptr_t)dpx | (uintptr_t)dlogits) & 15) != 0))
+    return false;
+#define CALLW(NV) softmax_vjp_wide_kernel<NV><<<(unsigned)rows, 256, 0, st>>>(px, dpx, V, dlogits)
+  EODM_DISPATCH_NV((V / 4 + 255) / 256, CALLW);
+#undef CALLW
   return cudaGetLastError() == cudaSuccess;
 }
 

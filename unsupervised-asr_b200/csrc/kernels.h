@@ -27,6 +27,7 @@ int eodm_loss_launch(const float* S, const float* N, const float* py, int K, flo
 int eodm_add_vectors_launch(const float* a, const float* b, int n, float* out, cudaStream_t st);
 int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st);
 bool eodm_softmax_rows4_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st);  // aux_ops.cu
+bool eodm_softmax_vjp_wide_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st);
 int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st);
 int eodm_prob_fwd_launch(const eodm_table* t, const float* px, int B, int T, float* p, cudaStream_t st);
 int eodm_prob_bwd_launch(const eodm_table* t, const float* px, const float* dp, int B, int T, float* dpx,

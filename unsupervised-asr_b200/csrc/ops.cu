@@ -271,6 +271,7 @@ int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px,
 
 int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int V, float* dlogits, cudaStream_t st) {
   if (rows == 0) return EODM_OK;
+  if (eodm_softmax_vjp_wide_launch(px, dpx, rows, V, dlogits, st)) return EODM_OK;   // 128 < V <= 8192: a CTA per row
   const int G = vec_group(V);
   if (G && (((uintptr_t)px | (uintptr_t)dpx | (uintptr_t)dlogits) & 15) == 0 && rows * G / 256 < 0x7fffffffLL) {
     EODM_SOFTMAX_DISPATCH(eodm_softmax_bwd_vec_kernel, G, px, dpx, rows, V, dlogits);

@@ -269,9 +269,9 @@ class _EodmLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         px, gS = ctx.saved_tensors
-        dpx = counts_bwd(ctx.table, px, ctx.mask, gS)
-        dlogits = softmax_bwd(px, dpx)
-        return dlogits * gout, None, None, None, None
+        # everything below is linear in gS: the upstream gradient scales K floats, not [B, T, V]
+        dpx = counts_bwd(ctx.table, px, ctx.mask, gS * gout)
+        return softmax_bwd(px, dpx), None, None, None, None
 
 
 class PNgram:
@@ -411,9 +411,10 @@ class _DenseBigramLossFn(torch.autograd.Function):
         px, gS = ctx.saved_tensors
         V = ctx.table.V
         G = torch.empty((V, V), dtype=torch.float32, device=px.device)
+        gS = _f32c(gS * gout, "gS")                                 # linear in gS: scale K floats, not [B, T, V]
         check(lib.eodm_bigram_scatter(ctx.table._h, _ptr(gS), _ptr(G), _stream()))
         dpx = bigram_dense_bwd(px, ctx.mask, G)
-        return softmax_bwd(px, dpx) * gout, None, None, None, None
+        return softmax_bwd(px, dpx), None, None, None, None
 
 
 def EODM_loss_dense_bigram(_logits, mask, conv_op, k, py):
