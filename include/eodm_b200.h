@@ -199,6 +199,15 @@ int eodm_host_free(void* p);
 int eodm_session_loss(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
                       void* comm, float* loss_host, float* dlogits_host);
 
+/* The same step without waiting for it: two steps can be in flight (slot 0 and slot 1).  Step i+1's host->device
+ * copy and step i-1's device->host copy run on their own streams while step i computes, so a stream of independent
+ * batches is bound by the compute alone.  The host buffers must stay valid (and pinned, to overlap) until
+ * eodm_session_wait(slot) returns; a slot can be submitted again only after it has been waited for.  With a
+ * communicator or a peer group every rank must submit in the same order. */
+int eodm_session_submit(eodm_session* s, int slot, const float* logits_host, const uint8_t* mask_host, int B, int T,
+                        void* comm, float* loss_host, float* dlogits_host);
+int eodm_session_wait(eodm_session* s, int slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -566,3 +566,35 @@ def test_legacy_partial_sums(eodm):
     K_sum = sum(k for _, k in parts)
     assert torch.all(K_sum == K_ref)
     assert rel_max((pz_sum / K_sum).cpu().numpy(), S_ref / K_ref) <= TOL
+
+
+def test_session_submit_wait_matches_synchronous_call(eodm):
+    """Two steps in flight (eodm_session_submit / eodm_session_wait) give the bits of the synchronous call, whatever the
+    interleaving, for batches large enough to take the two-half pipeline and for small ones."""
+    from eodm_b200.session import PinnedArray
+    dev = _dev()
+    for (V, n, K, B, T) in [(48, 3, 3000, 64, 400), (40, 5, 500, 3, 30)]:
+        ids, py = O.synth_table(V, n, K, seed=11)
+        table = eodm.NgramTable.from_ids(ids, V, device=0)
+        sess = eodm.Session(table, py, B, T)
+        rng = np.random.default_rng(5)
+        batches = []
+        for i in range(5):
+            lg = PinnedArray((B, T, V), np.float32); lg.array[...] = rng.standard_normal((B, T, V)) * (1 + i)
+            mk = PinnedArray((B, T), np.uint8); mk.array[...] = (rng.random((B, T)) < 0.9)
+            dl = PinnedArray((B, T, V), np.float32); ls = PinnedArray((1,), np.float32)
+            batches.append((lg, mk, dl, ls))
+        ref = []
+        for lg, mk, dl, ls in batches:
+            out = np.empty((B, T, V), np.float32)
+            ref.append((sess.loss(lg.array, mk.array, out), out))
+        sess.submit(0, batches[0][0].array, batches[0][1].array, batches[0][3].array, batches[0][2].array)
+        for i in range(1, 5):
+            sess.submit(i & 1, batches[i][0].array, batches[i][1].array, batches[i][3].array, batches[i][2].array)
+            sess.wait((i - 1) & 1)
+        sess.wait(0)
+        for (l_ref, d_ref), (lg, mk, dl, ls) in zip(ref, batches):
+            assert float(ls.array[0]) == l_ref and np.array_equal(dl.array, d_ref)
+        with pytest.raises(eodm.EodmError):
+            sess.wait(1)                                          # nothing in flight
+        sess.close()

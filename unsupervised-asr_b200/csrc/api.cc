@@ -238,6 +238,16 @@ struct eodm_session {
   uint8_t* mask;
   void* ws;
   eodm_peer* peer;   // when set: the exchange + loss run as one kernel over peer memory (peer.cu)
+  // submit/wait (two steps in flight): per-slot input / output buffers and events, allocated at the first submit;
+  // px, dpx, counts, gS and the workspace are shared -- they are only touched on the in-order compute stream
+  struct Slot {
+    float *logits, *dlogits, *loss;
+    uint8_t* mask;
+    cudaEvent_t in[2], out[2], loss_ready, done;
+    bool busy;
+  } slot[2];
+  cudaStream_t h2d_st, d2h_st;
+  bool slots_ready;
 };
 
 static void session_free(eodm_session* s) {
@@ -250,6 +260,14 @@ static void session_free(eodm_session* s) {
     if (p) cudaFree(p);
   for (cudaEvent_t ev : {s->ev_in[0], s->ev_in[1], s->ev_out[0], s->ev_out[1], s->ev_done})
     if (ev) cudaEventDestroy(ev);
+  for (auto& sl : s->slot) {
+    for (void* p : {(void*)sl.logits, (void*)sl.dlogits, (void*)sl.loss, (void*)sl.mask})
+      if (p) cudaFree(p);
+    for (cudaEvent_t ev : {sl.in[0], sl.in[1], sl.out[0], sl.out[1], sl.loss_ready, sl.done})
+      if (ev) cudaEventDestroy(ev);
+  }
+  if (s->h2d_st) cudaStreamDestroy(s->h2d_st);
+  if (s->d2h_st) cudaStreamDestroy(s->d2h_st);
   if (s->copy_st) cudaStreamDestroy(s->copy_st);
   if (s->st) cudaStreamDestroy(s->st);
   if (prev >= 0) cudaSetDevice(prev);
@@ -430,6 +448,110 @@ extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, cons
   if (rc != EODM_OK) return rc;
   if (e != cudaSuccess) {
     eodm_set_error("eodm_session_loss: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// submit / wait: two steps in flight.  Step i+1's host->device copy and step i-1's device->host copy run on their own
+// streams (the GPU's two copy engines) while step i computes; the compute stream stays in order, so the exchange of
+// a multi-GPU step is issued in submit order on every rank.
+// ---------------------------------------------------------------------------
+static int session_slots_init(eodm_session* s) {
+  if (s->slots_ready) return EODM_OK;
+  const size_t rows = (size_t)s->maxB * s->maxT, el = rows * s->t->V * sizeof(float);
+  cudaError_t e = cudaStreamCreateWithFlags(&s->h2d_st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->d2h_st, cudaStreamNonBlocking);
+  for (auto& sl : s->slot) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sl.logits, el);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sl.dlogits, el);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sl.mask, rows);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sl.loss, 256);
+    for (cudaEvent_t* ev : {&sl.in[0], &sl.in[1], &sl.out[0], &sl.out[1], &sl.loss_ready, &sl.done})
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_session_submit: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? EODM_ENOMEM : EODM_ECUDA;
+  }
+  s->slots_ready = true;
+  return EODM_OK;
+}
+
+extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logits_host, const uint8_t* mask_host, int B,
+                                   int T, void* comm, float* loss_host, float* dlogits_host) {
+  REQUIRE(s && logits_host && mask_host && loss_host, EODM_EINVAL, "null pointer");
+  REQUIRE(slot == 0 || slot == 1, EODM_EINVAL, "slot %d (two steps can be in flight: 0 or 1)", slot);
+  REQUIRE(B >= 1 && B <= s->maxB && T >= s->t->n && T <= s->maxT, EODM_ESHAPE,
+          "batch [%d,%d] does not fit the session's [%d,%d] (kernel_size %d)", B, T, s->maxB, s->maxT, s->t->n);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(s->device));
+  int rc = session_slots_init(s);
+  if (rc != EODM_OK) return rc;
+  eodm_session::Slot& sl = s->slot[slot];
+  REQUIRE(!sl.busy, EODM_EINVAL, "slot %d is still in flight: call eodm_session_wait first", slot);
+  const eodm_table* t = s->t;
+  const int V = t->V, K = t->K;
+  const int nch = (B >= 2 && (size_t)B * T * V * sizeof(float) >= ((size_t)2 << 20)) ? 2 : 1;
+  const int Bc[2] = {nch == 2 ? B / 2 : B, B - B / 2};
+  const size_t row0[2] = {0, (size_t)Bc[0] * T};
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < nch && e == cudaSuccess; ++c) {
+    const size_t rows = (size_t)Bc[c] * T;
+    e = cudaMemcpyAsync(sl.logits + row0[c] * V, logits_host + row0[c] * V, rows * V * sizeof(float),
+                        cudaMemcpyHostToDevice, s->h2d_st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.mask + row0[c], mask_host + row0[c], rows, cudaMemcpyHostToDevice, s->h2d_st);
+    if (e == cudaSuccess) e = cudaEventRecord(sl.in[c], s->h2d_st);
+  }
+  for (int c = 0; c < nch && e == cudaSuccess && rc == EODM_OK; ++c) {
+    e = cudaStreamWaitEvent(s->st, sl.in[c], 0);
+    if (e != cudaSuccess) break;
+    float* cc = nch == 2 ? s->counts2 + (size_t)c * (K + 1) : s->counts;
+    rc = eodm_softmax_fwd_launch(sl.logits + row0[c] * V, (int64_t)Bc[c] * T, V, s->px + row0[c] * V, s->st);
+    if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, sl.mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
+  }
+  if (e == cudaSuccess && rc == EODM_OK && nch == 2)
+    rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  if (e == cudaSuccess && rc == EODM_OK)
+    rc = session_exchange_and_loss(s, s->counts, comm, sl.loss, dlogits_host != nullptr, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(sl.loss_ready, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->d2h_st, sl.loss_ready, 0);
+  if (e == cudaSuccess && rc == EODM_OK)
+    e = cudaMemcpyAsync(loss_host, sl.loss, sizeof(float), cudaMemcpyDeviceToHost, s->d2h_st);
+  for (int c = 0; c < nch && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
+    const size_t rows = (size_t)Bc[c] * T;
+    rc = eodm_counts_bwd(t, s->px + row0[c] * V, sl.mask + row0[c], Bc[c], T, s->gS, s->dpx + row0[c] * V, s->ws, s->st);
+    if (rc == EODM_OK)
+      rc = eodm_softmax_bwd_launch(s->px + row0[c] * V, s->dpx + row0[c] * V, (int64_t)rows, V, sl.dlogits + row0[c] * V, s->st);
+    if (rc != EODM_OK) break;
+    e = cudaEventRecord(sl.out[c], s->st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->d2h_st, sl.out[c], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dlogits_host + row0[c] * V, sl.dlogits + row0[c] * V, rows * V * sizeof(float),
+                          cudaMemcpyDeviceToHost, s->d2h_st);
+  }
+  if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(sl.done, s->d2h_st);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (rc != EODM_OK) return rc;
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_session_submit: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  sl.busy = true;
+  return EODM_OK;
+}
+
+extern "C" int eodm_session_wait(eodm_session* s, int slot) {
+  REQUIRE(s, EODM_EINVAL, "null pointer");
+  REQUIRE(slot == 0 || slot == 1, EODM_EINVAL, "slot %d", slot);
+  eodm_session::Slot& sl = s->slot[slot];
+  REQUIRE(s->slots_ready && sl.busy, EODM_EINVAL, "nothing was submitted in slot %d", slot);
+  const cudaError_t e = cudaEventSynchronize(sl.done);
+  sl.busy = false;
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_session_wait: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
   }
   return EODM_OK;

@@ -55,6 +55,8 @@ SIGNATURES = {
     "eodm_peer_loss": (_i, [_p, _p, _p, C.c_float, _p, _p, _p, _p]),
     "eodm_peer_failed": (_i, [_p]),
     "eodm_session_set_peer": (_i, [_p, _p]),
+    "eodm_session_submit": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p]),
+    "eodm_session_wait": (_i, [_p, _i]),
     "eodm_counts_partial": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_counts_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_loss_from_counts": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _p]),

@@ -63,6 +63,25 @@ class Session:
                                     self._loss.ctypes.data_as(C.c_void_p), dptr))
         return float(self._loss[0])
 
+    def submit(self, slot, logits, mask, loss_out, dlogits_out=None, comm=None):
+        """Enqueue a step without waiting (slot 0 or 1; see eodm_session_submit).  loss_out: float32[1] host array that
+        receives the loss; all host arrays must stay alive until wait(slot)."""
+        B, T, V = logits.shape
+        assert logits.dtype == np.float32 and logits.flags.c_contiguous
+        m = mask.view(np.uint8) if mask.dtype == np.bool_ else mask
+        assert m.dtype == np.uint8 and m.flags.c_contiguous and m.shape == (B, T)
+        assert loss_out.dtype == np.float32 and loss_out.size >= 1
+        dptr = None
+        if dlogits_out is not None:
+            assert dlogits_out.dtype == np.float32 and dlogits_out.flags.c_contiguous and dlogits_out.shape == logits.shape
+            dptr = dlogits_out.ctypes.data_as(C.c_void_p)
+        check(lib.eodm_session_submit(self._h, int(slot), logits.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p),
+                                      B, T, comm.handle if comm is not None else None,
+                                      loss_out.ctypes.data_as(C.c_void_p), dptr))
+
+    def wait(self, slot):
+        check(lib.eodm_session_wait(self._h, int(slot)))
+
     def set_peer(self, group):
         """Use a dist.PeerGroup for the exchange of the following steps (None to undo)."""
         check(lib.eodm_session_set_peer(self._h, group.handle if group is not None else None))
