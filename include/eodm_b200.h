@@ -141,6 +141,9 @@ int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B, int T, in
 /* dpx from upstream G f32[V][V] = dloss/dC. */
 int eodm_bigram_dense_bwd(const float* px, const uint8_t* mask, int B, int T, int V, const float* G, float* dpx,
                           void* ws, void* stream);
+/* The same VJP right after eodm_bigram_dense_fwd on the SAME workspace: the operand planes that call left in `ws` are
+ * reused instead of rebuilt.  The caller vouches that `ws` still holds them (same px, mask, B, T, V; untouched since). */
+int eodm_bigram_dense_bwd_prepared(int B, int T, int V, const float* G, float* dpx, void* ws, void* stream);
 
 /* The prior's K bigrams inside the dense matrices, for a kernel_size-2 table: S[z] = C[ids[z]] (gather, then
  * eodm_allreduce_counts moves K+1 floats instead of V*V) and G = scatter(gS) (duplicated table entries add up). */

@@ -339,7 +339,10 @@ def test_dense_bigram_tcgen05_vs_oracle(eodm, B, T, V, ragged):
     d_ref = O.bigram_dense_bwd(px64, mask, G.astype(np.float64))
     assert rel_max(d, d_ref) <= TOL and rel_l2(d, d_ref) <= TOL
     # bit-reproducible
-    assert torch.equal(Cm, eodm.bigram_dense_fwd(px, m)[0])
+    Cm2, _, ws = eodm.bigram_dense_fwd(px, m, return_ws=True)
+    assert torch.equal(Cm, Cm2)
+    # the VJP on the forward's workspace (operand planes reused) gives the bits of the stand-alone VJP
+    assert torch.equal(eodm.bigram_dense_bwd(px, m, torch.tensor(G, device=dev), ws=ws), torch.tensor(d, device=dev))
     with pytest.raises(eodm.EodmError) as e:
         eodm.bigram_dense_fwd(px[:, :, :100].contiguous(), m)       # V not a multiple of 128
     assert e.value.status == -5

@@ -360,9 +360,10 @@ def EODM_loss(_logits, mask, conv_op, k, py):
 # ---------------------------------------------------------------------------
 # dense bigram contraction for large vocabularies (tcgen05 path)
 # ---------------------------------------------------------------------------
-def bigram_dense_fwd(px, mask):
+def bigram_dense_fwd(px, mask, return_ws=False):
     """C[u, v] = sum_{b, t<=T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps), f32[V, V]; N = sum(mask).
-    V must be a multiple of 128."""
+    V must be a multiple of 128.  return_ws: also return the workspace, whose operand planes bigram_dense_bwd can
+    reuse (`ws=`) as long as px and mask are the same."""
     px = _f32c(px, "px")
     B, T, V = px.shape
     mask = _mask_u8(mask, px.device)
@@ -370,11 +371,12 @@ def bigram_dense_fwd(px, mask):
     N = torch.empty(1, dtype=torch.float32, device=px.device)
     ws = torch.empty(max(lib.eodm_bigram_workspace_bytes(B, T, V), 256), dtype=torch.uint8, device=px.device)
     check(lib.eodm_bigram_dense_fwd(_ptr(px), _ptr(mask), B, T, V, _ptr(Cm), _ptr(N), _ptr(ws), _stream()))
-    return Cm, N
+    return (Cm, N, ws) if return_ws else (Cm, N)
 
 
-def bigram_dense_bwd(px, mask, G):
-    """dpx f32[B, T, V] for an upstream G = dloss/dC f32[V, V]."""
+def bigram_dense_bwd(px, mask, G, ws=None):
+    """dpx f32[B, T, V] for an upstream G = dloss/dC f32[V, V].  ws: the workspace bigram_dense_fwd(..., return_ws=True)
+    returned for the same px and mask -- its operand planes are reused instead of rebuilt."""
     px = _f32c(px, "px")
     B, T, V = px.shape
     mask = _mask_u8(mask, px.device)
@@ -382,6 +384,9 @@ def bigram_dense_bwd(px, mask, G):
     if tuple(G.shape) != (V, V):
         raise EodmError(_lib.ESHAPE, "G must be [%d, %d], got %r" % (V, V, tuple(G.shape)))
     dpx = torch.empty_like(px)
+    if ws is not None:
+        check(lib.eodm_bigram_dense_bwd_prepared(B, T, V, _ptr(G), _ptr(dpx), _ptr(ws), _stream()))
+        return dpx
     ws = torch.empty(max(lib.eodm_bigram_workspace_bytes(B, T, V), 256), dtype=torch.uint8, device=px.device)
     check(lib.eodm_bigram_dense_bwd(_ptr(px), _ptr(mask), B, T, V, _ptr(G), _ptr(dpx), _ptr(ws), _stream()))
     return dpx
@@ -392,7 +397,7 @@ class _DenseBigramLossFn(torch.autograd.Function):
     def forward(ctx, logits, mask, py, table, comm):
         logits = _f32c(logits, "_logits")
         px = softmax_fwd(logits)
-        Cm, N = bigram_dense_fwd(px, mask)                         # all V*V expected bigram counts (tcgen05)
+        Cm, N, ws = bigram_dense_fwd(px, mask, return_ws=True)     # all V*V expected bigram counts (tcgen05)
         counts = torch.empty(table.K + 1, dtype=torch.float32, device=px.device)
         check(lib.eodm_bigram_gather(table._h, _ptr(Cm), _ptr(counts), _stream()))
         counts[table.K:] = N
@@ -402,7 +407,7 @@ class _DenseBigramLossFn(torch.autograd.Function):
             if comm is not None:
                 comm.allreduce_counts(counts, table.K)             # K+1 floats, not V*V
             loss, gS = loss_from_counts(counts, py, table.K, True)
-        ctx.table, ctx.mask = table, mask
+        ctx.table, ctx.mask, ctx.ws = table, mask, ws            # the VJP reuses the operand planes left in ws
         ctx.save_for_backward(px, gS)
         return loss.reshape(())
 
@@ -413,7 +418,8 @@ class _DenseBigramLossFn(torch.autograd.Function):
         G = torch.empty((V, V), dtype=torch.float32, device=px.device)
         gS = _f32c(gS * gout, "gS")                                 # linear in gS: scale K floats, not [B, T, V]
         check(lib.eodm_bigram_scatter(ctx.table._h, _ptr(gS), _ptr(G), _stream()))
-        dpx = bigram_dense_bwd(px, ctx.mask, G)
+        dpx = bigram_dense_bwd(px, ctx.mask, G, ws=ctx.ws)
+        ctx.ws = None
         return softmax_bwd(px, dpx), None, None, None, None
 
 

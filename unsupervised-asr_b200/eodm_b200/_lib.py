@@ -73,6 +73,7 @@ SIGNATURES = {
     "eodm_bigram_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "eodm_bigram_dense_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "eodm_bigram_dense_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "eodm_bigram_dense_bwd_prepared": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "eodm_bigram_gather": (_i, [_p, _p, _p, _p]),
     "eodm_bigram_scatter": (_i, [_p, _p, _p, _p]),
     "eodm_allreduce_counts": (_i, [_p, _p, _i, _p, _p]),
