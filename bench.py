@@ -375,7 +375,7 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
                        "exchange": None if world == 1 else
                        ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
-                       "path": "cuda-core trie walk (v2)"},
+                       "path": "cuda-core trie walk (shared-memory operand tile, flat tails, node stream two entries ahead)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }
