@@ -292,3 +292,22 @@ def test_no_cpu_fallback(eodm):
         for f in fs:
             if f.endswith((".py", ".cc", ".cu", ".h")):
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace("# oracle-free", ""), f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): stdout is exactly one JSON record with the
+    contract's keys, on the reference's own CPU-runnable shape; needs no GPU and no CUDA library."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "timit_ref",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "EODM fwd+bwd frames/sec" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "timit_ref"
