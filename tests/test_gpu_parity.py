@@ -159,6 +159,53 @@ def test_tensor_core_counts_vs_oracle(eodm, seed, V, n, K, B, T):
     assert (np.abs(counts[:K] - S_ref) / S_ref).max() <= TOL
 
 
+@pytest.mark.parametrize("seed,V,K,B,T,len_lo,dup", [
+    (1, 48, 10000, 6, 100, None, False),     # BASELINE configs[1] table; 600 rows = 4.8 tiles of 126
+    (2, 48, 3000, 40, 300, 3, True),         # ragged, duplicates, 96 tiles: several tile pairs per CTA pair
+    (3, 40, 5000, 7, 131, 1, False),         # V padded 40 -> 48; lengths down to 1 (< kernel size)
+    (4, 30, 2000, 5, 64, 5, True),           # V padded to 32 (one phase per block)
+    (5, 64, 20000, 3, 257, 10, False),       # V = 64: 16 blocks per GEMM
+    (6, 50, 8000, 2, 90, None, False),       # V padded 50 -> 64
+    (7, 12, 500, 9, 3, None, False),         # T == kernel size: one window per utterance; V padded to 16
+    (8, 47, 9000, 1, 126, None, False),      # exactly one tile, V % 4 != 0 (scalar staging)
+    (9, 48, 10000, 148, 400, 200, False),    # 470 tiles: more than three tile pairs per CTA pair
+])
+def test_tensor_core_vjp_vs_oracle(eodm, seed, V, K, B, T, len_lo, dup):
+    """The tcgen05 VJP of a trigram-only table (csrc/tcbwd.cu: windows on the M axis, 3xTF32, cta_group::2), pinned
+    through the debug hook, against the fp64 oracle; bit-reproducible; and agreeing with the CUDA-core walk."""
+    from eodm_b200._lib import lib
+    from oracle import fast as F
+    ids, py = eodm.synth.table(V, 3, K, seed=seed, min_id=0 if seed % 2 else 1)
+    if dup:
+        ids[K // 2] = ids[0]
+        ids[K - 1] = ids[0]
+        ids[K - 2] = ids[1]
+    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=len_lo)
+    if B > 2:
+        mask[1, :] = False
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    m = torch.tensor(mask, device=dev)
+    gS = np.random.default_rng(seed).standard_normal(K).astype(np.float32)
+    gSt = torch.tensor(gS, device=dev)
+    d_ref = F.counts_bwd(px.cpu().numpy().astype(np.float64), mask, ids, 3, gS.astype(np.float64))
+    try:
+        lib.eodm_debug_set_path(2)
+        dpx = eodm.counts_bwd(table, px, m, gSt)
+        dpx2 = eodm.counts_bwd(table, px, m, gSt)
+        lib.eodm_debug_set_path(1)
+        walk = eodm.counts_bwd(table, px, m, gSt)
+    finally:
+        lib.eodm_debug_set_path(0)
+    assert torch.equal(dpx, dpx2)
+    got = dpx.cpu().numpy()
+    assert rel_max(got, d_ref) <= TOL and rel_l2(got, d_ref) <= TOL, (rel_max(got, d_ref), rel_l2(got, d_ref))
+    assert rel_max(walk.cpu().numpy(), d_ref) <= TOL
+    if B > 2:
+        assert not got[1].any()                  # a fully masked utterance receives exactly zero
+
+
 @pytest.mark.parametrize("seed,V,n,K,B,T,mixed,dup", [CASES[1], CASES[5], CASES[7]])
 def test_eodm_loss_end_to_end_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
     ids, py, logits, mask = _random_case(seed, V, n, K, B, T, mixed, dup)

@@ -65,6 +65,36 @@ def test_oracle_direct_matches_reference_graph(golden, tag):
     assert np.allclose(pz, golden[tag + "_pz_f64"], rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_c_oracle_matches_reference_graph_and_numpy_oracle(golden, tag):
+    """oracle/eodm_oracle_c.c (the fp64 scalar-loop restatement used at the full BASELINE sizes) against the goldens
+    generated from the reference's own source, and against the numpy oracle on a mixed-order table."""
+    from oracle import fast as F
+    kernel, ids, py, n, logits, mask = _case(golden, tag)
+    r = F.eodm_loss_direct(logits, mask, ids, n, py)
+    assert abs(r["loss"] - golden[tag + "_loss_f64"]) <= 1e-12 * abs(golden[tag + "_loss_f64"])
+    ref = golden[tag + "_dlogits_f64"]
+    assert np.abs(r["dlogits"] - ref).max() <= 1e-10 * np.abs(ref).max()
+    ids2, py2 = O.synth_table(11, 4, 60, seed=3, min_id=0)
+    ids2[::5, 2:] = -1
+    ids2[1::7, 1:] = -1
+    ids2[7] = -1                                            # an all-zero column: pz == 1
+    lg, mk = O.synth_batch(6, 19, 11, seed=3, len_lo=1)
+    mk[0] = False
+    a, b = O.eodm_loss_direct(lg, mk, ids2, 4, py2), F.eodm_loss_direct(lg, mk, ids2, 4, py2)
+    assert abs(a["loss"] - b["loss"]) <= 1e-13 * abs(a["loss"]) and a["N"] == b["N"]
+    assert np.abs(a["S"] - b["S"]).max() <= 1e-13 * a["S"].max()
+    assert np.abs(a["dlogits"] - b["dlogits"]).max() <= 1e-12 * np.abs(a["dlogits"]).max()
+    with pytest.raises(ValueError):
+        F.counts_fwd(np.zeros((1, 3, 11)), np.ones((1, 3), bool), ids2, 4)       # T < kernel_size
+    # per-order tables summed (SURVEY 8d config 3) == the numpy oracle per table
+    tabs = [O.synth_table(11, o, 10, seed=o, min_id=0) for o in (1, 2, 3)]
+    m = F.multi_order_loss_direct(lg, mk, tabs)
+    want = [O.eodm_loss_direct(lg, mk, t[0], t[0].shape[1], t[1]) for t in tabs]
+    assert abs(m["loss"] - sum(w["loss"] for w in want)) <= 1e-12 * abs(m["loss"])
+    assert np.abs(m["dlogits"] - sum(w["dlogits"] for w in want)).max() <= 1e-12 * np.abs(m["dlogits"]).max()
+
+
 @pytest.mark.parametrize("tag", ["A", "C"])
 def test_oracle_literal_fp32_matches_reference_graph(golden, tag):
     kernel, ids, py, n, logits, mask = _case(golden, tag)

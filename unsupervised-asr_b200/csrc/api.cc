@@ -58,12 +58,26 @@ static bool use_tensor_fwd(const eodm_table* t) {
 }
 
 static size_t counts_ws_aligned(const eodm_table* t) { return (eodm_counts_workspace_bytes(t) + 255) & ~(size_t)255; }
+static size_t tc_ws_aligned(const eodm_table* t) { return (eodm_tc_workspace_bytes(t) + 255) & ~(size_t)255; }
+
+// The tensor-core VJP (tcbwd.cu) costs 2 * ceil(VP^2/256) * (VP/8) * 3 MMAs of 128 clk per 126 rows whatever the table
+// holds; the trie walk costs about one shared-memory wavefront per (trie node, 32 rows) in each of its three tries.
+// Dense tables (BASELINE configs[1]: 10 000 of 47^3 trigrams) go to the tensor cores, sparse ones stay on the walk.
+static bool use_tensor_bwd(const eodm_table* t) {
+  if (!eodm_tcb_supported(t)) return false;
+  if (g_path == 1) return false;
+  if (g_path == 2) return true;
+  const double vp = t->tcb.vp;
+  const double tc_clk_per_row = 2.0 * ((vp * vp + 255) / 256) * (vp / 8) * 3 * 128 / 126 * 1.2;
+  const double walk_clk_per_row = (double)t->total_nodes_bwd / 32 / 0.8;
+  return tc_clk_per_row < walk_clk_per_row;
+}
 
 extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
   (void)B;
   (void)T;
   if (!t || t->device < 0) return 0;
-  return counts_ws_aligned(t) + eodm_tc_workspace_bytes(t);
+  return counts_ws_aligned(t) + tc_ws_aligned(t) + eodm_tcb_workspace_bytes(t);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -91,6 +105,9 @@ extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
+  if (use_tensor_bwd(t))
+    return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t) + tc_ws_aligned(t),
+                           (cudaStream_t)stream);
   return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream);
 }
 

@@ -3,6 +3,7 @@
 // as frozen Conv1D weights (models/EODM.py:64-70) built by ngram2kernel
 // (utils/tools.py:365-374).
 #include "table.h"
+#include "kernels.h"
 
 #include <cuda_runtime_api.h>
 #include <stdarg.h>
@@ -399,6 +400,40 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
     if (rc == EODM_OK) {
       rc = upload(t, is_first, &d);
       t->d_is_first = (int32_t*)d;
+    }
+  }
+  t->tcb = EodmTcb{0, nullptr, nullptr, 0};
+  if (rc == EODM_OK && !host_only) {
+    const int vp = eodm_tcb_vp(n, V, t->full_order);
+    if (vp > 0) {
+      // first table entry of every trigram, and the chains of its duplicates in table order
+      std::vector<int32_t> first((size_t)V * V * V, -1), last((size_t)V * V * V, -1), next(K, -1);
+      for (int z = 0; z < K; ++z) {
+        const size_t key = ((size_t)ids[(size_t)z * 3] * V + ids[(size_t)z * 3 + 1]) * V + ids[(size_t)z * 3 + 2];
+        if (first[key] < 0) first[key] = z;
+        else next[last[key]] = z;
+        last[key] = z;
+      }
+      // image order: GEMM g, block j of 256 pairs, K-step ks, CTA rank, 16-byte chunk q, pair row, element e
+      const int nb = (vp * vp + 255) / 256, ksn = vp / 8;
+      std::vector<int32_t> zmap((size_t)2 * nb * ksn * 2 * 1024, -1);
+      size_t i = 0;
+      for (int g = 0; g < 2; ++g)
+        for (int j = 0; j < nb; ++j)
+          for (int ks = 0; ks < ksn; ++ks)
+            for (int r = 0; r < 2; ++r)
+              for (int q = 0; q < 2; ++q)
+                for (int row = 0; row < 128; ++row)
+                  for (int e = 0; e < 4; ++e, ++i) {
+                    const int pr = j * 256 + r * 128 + row, k = ks * 8 + q * 4 + e;
+                    const int x = pr / vp, y = pr % vp;
+                    // GEMM 1: pairs (a,b), reduction c;  GEMM 2: pairs (b,c), reduction a
+                    const int a = g == 0 ? x : k, b = g == 0 ? y : x, c = g == 0 ? k : y;
+                    if (pr < vp * vp && a < V && b < V && c < V) zmap[i] = first[((size_t)a * V + b) * V + c];
+                  }
+      t->tcb.vp = vp;
+      t->tcb.zmap_len = (int64_t)zmap.size();
+      if ((rc = upload(t, zmap, &t->tcb.d_zmap)) == EODM_OK) rc = upload(t, next, &t->tcb.d_next);
     }
   }
   for (int j = 0; j < EODM_MAX_N; ++j) t->rows[j] = EodmRows{0, nullptr, nullptr, nullptr};

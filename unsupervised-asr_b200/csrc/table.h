@@ -80,6 +80,16 @@ struct EodmRows {
   const int32_t* d_zcol;  // [K]
 };
 
+// Tensor-core VJP (tcbwd.cu): trigram-only tables over V <= 64.  zmap lists, in the order the kernel's stages consume
+// the dense G[a,b,c] image, the first table entry that is the trigram of each image element (-1: none); next chains
+// the duplicates of an entry in table order.
+struct EodmTcb {
+  int vp;                 // V padded to 16 / 32 / 48 / 64; 0 = the path does not apply
+  const int32_t* d_zmap;  // [zmap_len]
+  const int32_t* d_next;  // [K]
+  int64_t zmap_len;
+};
+
 struct eodm_table {
   int n, V, K, device;        // device == -1: host-only table (no uploads; compute calls reject it)
   EodmTrieHost htrie[EODM_MAX_N];
@@ -105,6 +115,7 @@ struct eodm_table {
   int32_t* d_is_first;        //     dense-bigram scatter; d_is_first[z] = 1 if z heads its chain
   bool full_order;            // every n-gram has order == n
   EodmRows rows[EODM_MAX_N];
+  EodmTcb tcb;
   int64_t node_offset[EODM_MAX_N];
   int64_t total_nodes_padded;
   std::vector<void*> allocs;  // every device allocation, for destroy
