@@ -46,5 +46,11 @@ for path, tag in ((1, "walk"), (2, "tc")):
         out["fwd_" + tag + "_ms"] = timed(lambda: E.counts_fwd(table, px, m))
     except E.EodmError as e:
         out["err_" + tag] = str(e)
+if len(sys.argv) > 2:      # timing experiments of the tensor-core VJP (results are wrong with a switch on)
+    lib.eodm_debug_set_path(2)
+    for dbg in (1, 2, 3):
+        lib.eodm_debug_tcb_switches(dbg)
+        out["bwd_tc_dbg%d_ms" % dbg] = timed(lambda: E.counts_bwd(table, px, m, gS))
+    lib.eodm_debug_tcb_switches(0)
 lib.eodm_debug_set_path(0)
 print(json.dumps(out))

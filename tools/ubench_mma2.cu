@@ -67,21 +67,23 @@ __global__ void __launch_bounds__(128, 1) k_time1(int M, int N, int iters, long 
 }
 
 // ---------------------------------------------------------------- (1b) cta_group::2 timing
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_time2(int M, int N, int iters, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_time2(int M, int N, int iters, long long* out, int a_rs = 0, int a_shift = 0, int d_step = 256, int commit_every = 0) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
   __shared__ uint32_t slot;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   float* B = reinterpret_cast<float*>(smem);       // this CTA's N/2 rows
   float* A = B + 128 * 8;                          // this CTA's M/2 rows
-  for (int i = threadIdx.x; i < 128 * 8 + 128 * 8; i += 128) B[i] = 1.0f;
+  for (int i = threadIdx.x; i < 128 * 8 + 136 * 8; i += 128) B[i] = 1.0f;
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -93,13 +95,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_time2(int 
   if (threadIdx.x == 0 && rank == 0) {
     const uint32_t idesc = idesc_tf32(M, N);
     const uint64_t bd = desc_k(smem_u32(B), (uint32_t)(N / 2) * 16u, 128u);
-    const uint64_t ad = desc_k(smem_u32(A), (uint32_t)(M / 2) * 16u, 128u);
+    const uint64_t ad = a_rs ? desc_k(smem_u32(A) + (uint32_t)a_shift * 16u, (uint32_t)a_rs * 16u, 128u)
+                             : desc_k(smem_u32(A), (uint32_t)(M / 2) * 16u, 128u);
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tmem + (uint32_t)((i & 1) * 256);
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                   ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+    const uint32_t d0 = tmem, d1 = tmem + (uint32_t)d_step;
+#define MMA2(D) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" \
+                   ::"r"(D), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory")
+    if (commit_every == 0) {
+      for (int i = 0; i < iters; i += 6) { MMA2(d0); MMA2(d1); MMA2(d0); MMA2(d1); MMA2(d0); MMA2(d1); }
+    } else if (commit_every == 6) {
+      for (int i = 0; i < iters; i += 6) {
+        MMA2(d0); MMA2(d1); MMA2(d0); MMA2(d1); MMA2(d0); MMA2(d1);
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
+      }
+    } else {
+      for (int i = 0; i < iters; i += 6) {
+        MMA2(d0); MMA2(d1); MMA2(d0);
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
+        MMA2(d1); MMA2(d0); MMA2(d1);
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
+      }
     }
+#undef MMA2
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
     mbar_wait(&bar, 0);
@@ -183,8 +203,8 @@ static bool ok(const char* what) {
 
 int main() {
   long long* out; cudaMallocManaged(&out, 16);
-  const int iters = 4096;
-  const size_t sm = (256 * 8 + 128 * 8) * 4 + 256;
+  const int iters = 4092;
+  const size_t sm = (256 * 8 + 136 * 8) * 4 + 256;
   for (int M : {64, 128})
     for (int N : {64, 128, 256}) {
       for (int rep = 0; rep < 2; ++rep) { k_time1<<<148, 128, sm>>>(M, N, iters, out); if (!ok("time1")) return 1; }
@@ -195,6 +215,22 @@ int main() {
       for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(M, N, iters, out); if (!ok("time2")) return 1; }
       printf("cta_group::2 M=%3d N=%3d: %.1f clk/MMA (per pair)\n", M, N, (double)out[0] / iters);
     }
+  for (int sh : {0, 1, 2, 4, 8}) {
+    for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(256, 256, iters, out, 130, sh); if (!ok("time2s")) return 1; }
+    printf("cta_group::2 M=256 N=256, A in a 130-row buffer (LBO 2080 B) shifted by %d rows: %.1f clk/MMA\n", sh, (double)out[0] / iters);
+  }
+  for (int rs : {128, 132, 136}) {
+    for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(256, 256, iters, out, rs, 0); if (!ok("time2s")) return 1; }
+    printf("cta_group::2 M=256 N=256, A row stride %d (LBO %d B), no shift: %.1f clk/MMA\n", rs, rs * 16, (double)out[0] / iters);
+  }
+  for (int ce : {0, 6, 3}) {
+    for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(256, 128, iters, out, 130, 2, 128, ce); if (!ok("time2c")) return 1; }
+    printf("cta_group::2 M=256 N=128, D alternating at +128 columns, commit every %d MMAs: %.1f clk/MMA\n", ce, (double)out[0] / iters);
+  }
+  for (int ce : {0, 3}) {
+    for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(256, 256, iters, out, 130, 2, 0, ce); if (!ok("time2c")) return 1; }
+    printf("cta_group::2 M=256 N=256, ONE accumulator, commit every %d MMAs: %.1f clk/MMA\n", ce, (double)out[0] / iters);
+  }
   // (2)+(3)
   for (int cfg = 0; cfg < 3; ++cfg) {
     const int M = cfg == 2 ? 64 : 128, N = 64, KQ = 12, RS = cfg == 0 ? 128 : 130, shift = cfg == 0 ? 0 : 2;

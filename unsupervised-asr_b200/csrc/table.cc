@@ -414,23 +414,25 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
         else next[last[key]] = z;
         last[key] = z;
       }
-      // image order: GEMM g, block j of 256 pairs, K-step ks, CTA rank, 16-byte chunk q, pair row, element e
-      const int nb = (vp * vp + 255) / 256, ksn = vp / 8;
-      std::vector<int32_t> zmap((size_t)2 * nb * ksn * 2 * 1024, -1);
+      // image order: GEMM g, block j of 256 pairs, stage (two K-steps), CTA rank, K-step inside the stage, 16-byte
+      // chunk q, pair row, element e
+      const int nb = (vp * vp + 255) / 256, spb = vp / 16;
+      std::vector<int32_t> zmap((size_t)2 * nb * spb * 2 * 2048, -1);
       size_t i = 0;
       for (int g = 0; g < 2; ++g)
         for (int j = 0; j < nb; ++j)
-          for (int ks = 0; ks < ksn; ++ks)
+          for (int st = 0; st < spb; ++st)
             for (int r = 0; r < 2; ++r)
-              for (int q = 0; q < 2; ++q)
-                for (int row = 0; row < 128; ++row)
-                  for (int e = 0; e < 4; ++e, ++i) {
-                    const int pr = j * 256 + r * 128 + row, k = ks * 8 + q * 4 + e;
-                    const int x = pr / vp, y = pr % vp;
-                    // GEMM 1: pairs (a,b), reduction c;  GEMM 2: pairs (b,c), reduction a
-                    const int a = g == 0 ? x : k, b = g == 0 ? y : x, c = g == 0 ? k : y;
-                    if (pr < vp * vp && a < V && b < V && c < V) zmap[i] = first[((size_t)a * V + b) * V + c];
-                  }
+              for (int kk = 0; kk < 2; ++kk)
+                for (int q = 0; q < 2; ++q)
+                  for (int row = 0; row < 128; ++row)
+                    for (int e = 0; e < 4; ++e, ++i) {
+                      const int pr = j * 256 + r * 128 + row, k = (st * 2 + kk) * 8 + q * 4 + e;
+                      const int x = pr / vp, y = pr % vp;
+                      // GEMM 1: pairs (a,b), reduction c;  GEMM 2: pairs (b,c), reduction a
+                      const int a = g == 0 ? x : k, b = g == 0 ? y : x, c = g == 0 ? k : y;
+                      if (pr < vp * vp && a < V && b < V && c < V) zmap[i] = first[((size_t)a * V + b) * V + c];
+                    }
       t->tcb.vp = vp;
       t->tcb.zmap_len = (int64_t)zmap.size();
       if ((rc = upload(t, zmap, &t->tcb.d_zmap)) == EODM_OK) rc = upload(t, next, &t->tcb.d_next);

@@ -25,8 +25,9 @@
 // A CTA pair works on two adjacent tiles of 128 windows (tile stride 126 rows: a tile's output rows are the 126 rows
 // that receive all three window positions from windows of the same tile, so no sums cross CTAs -- deterministic, no
 // atomics).  Roles per CTA: warp 0 = TMA producer of the G image (one 8 KB box per stage and CTA, both CTAs'
-// transfers complete on the leader's barrier), warp 1 = MMA issuer (leader CTA only), warps 4-7 = epilogue (thread =
-// TMEM lane = window), warps 8-11 = staging of the next tile's posterior rows: E = px + eps as [k/4][row][4] planes
+// transfers complete on the leader's barrier), warps 1-2 = MMA issuers (leader CTA only, one per accumulator bank),
+// warps 4-11 = epilogue (thread = TMEM lane = window; two sets of four warps, one per half of a block's columns),
+// warp 3 = staging of the next tile's posterior rows: E = px + eps as [k/4][row][4] planes
 // (hi = E itself, lo) -- the canonical K-major no-swizzle layout with 16-byte rows, so "row w+2" (GEMM 1) and "row w"
 // (GEMM 2) are the SAME buffer read through descriptors whose start differs by 32 bytes.
 #include <cuda.h>
@@ -55,11 +56,13 @@ struct Cfg {
   static constexpr int NP = VP * VP;                // pair axis
   static constexpr int NB = (NP + 255) / 256;       // blocks of 256 pairs
   static constexpr int PH = VP / gcd_c(256, VP);    // distinct offsets of a block start inside a group of VP pairs
-  static constexpr int NST = VP > 48 ? 6 : 8;       // G stages (8 KB each per CTA)
+  static constexpr int SPB = KS / 2;                // stages per block: a stage holds two K-steps
+  static constexpr int NST = 4;                     // G stages (16 KB each per CTA)
   static constexpr int LDP = VP + 1;                // row stride of the dP tile (odd: lanes = rows never conflict)
   static constexpr uint32_t kPlane = (uint32_t)KQ * kRS * 16u;          // bytes of one E plane
-  static constexpr uint32_t kStage = 8192u;
-  static constexpr size_t kSmem = 4 * (size_t)kPlane + (size_t)NST * kStage + 128 * LDP * 4 + 2 * 128 + 1024;
+  static constexpr uint32_t kStage = 16384u;
+  static constexpr uint32_t kDpt = 128u * LDP * 4u;                    // bytes of one dP tile (one per epilogue set)
+  static constexpr size_t kSmem = 4 * (size_t)kPlane + (size_t)NST * kStage + 2 * (size_t)kDpt + 2 * 128 + 1024;
 };
 
 struct BArgs {
@@ -68,13 +71,66 @@ struct BArgs {
   float* dpx;
   long long NR;
   int T, V, n_tiles;
+  int px_tma;        // 1: the posterior tile is staged by TMA (V % 4 == 0), 0: by loads
+  long long* prof;   // debug: per-CTA cycle counters (eodm_debug_tcb_profile), nullptr in production
+  int dbg;           // debug (timing experiments only, results are wrong): 1 = no TMA, 2 = no epilogue work
+};
+
+// cycle counters of the profile buffer (per CTA, 16 slots)
+enum { kProfMmaFull = 0, kProfMmaDEmpty, kProfMmaAFull, kProfMmaTotal, kProfEpiDFull, kProfEpiAReady, kProfEpiWork, kProfEpiTotal,
+       kProfTmaEmpty, kProfTmaTotal, kProfStgFree, kProfStgTotal };
+// debug trace of CTA 0: clock64 at five events of every block (first 256 blocks), after the per-CTA counters
+constexpr int kTraceBase = 148 * 16, kTraceLen = 256;
+template <bool ON>
+__device__ __forceinline__ void trace(long long* prof_all, int ev, uint32_t blk) {
+  if (ON && prof_all && blockIdx.x == 0 && blk < (uint32_t)kTraceLen) prof_all[kTraceBase + ev * kTraceLen + blk] = clock64();
+}
+template <bool ON>
+struct ProfTimer {
+  long long* p;
+  long long t0;
+  __device__ __forceinline__ void start() { if (ON && p) t0 = clock64(); }
+  __device__ __forceinline__ void stop(int slot) { if (ON && p) p[slot] += clock64() - t0; }
 };
 
 struct BBars {
-  uint64_t full[8], empty[8], d_full[2], d_empty[2], a_full[2], a_ready[2], a_free[2];
+  uint64_t full[4], empty[4], d_full[2], d_empty[2], a_full[2], a_ready[2], a_free[2], p_full[2];
 };
 
-__device__ __forceinline__ void named_bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// "accumulator bank drained": the only thing ordered is tcgen05.ld before the next MMA's writes (tcgen05.fence on both
+// sides), no memory -- so the arrival carries CTA-scope release only.  A .release.cluster arrive costs a MEMBAR.ALL.GPU
+// (~1400 clk per block here, which made the epilogue slower than the MMAs; profiles/r02_tcbwd.md).
+__device__ __forceinline__ void mbar_arrive_cluster_light(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 rem;\n\t"
+      "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// cta_group::2 tf32 MMA from the LOW words of two K-major no-swizzle descriptors (address >> 4 | LBO >> 4 << 16); the
+// high word (SBO = 128 bytes, descriptor version 1) is the same for every operand of this kernel
+__device__ __forceinline__ void mma2_tf32_w(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(0x4008u)
+      : "memory");
+}
+
 
 // wait for the tcgen05.ld that produced r[]: the registers are operands, so no use of them can move above the wait
 __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
@@ -90,20 +146,24 @@ __device__ __forceinline__ float tf32_lo(float x) {
   return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
 }
 
-// ---- epilogue of one 256-column block of GEMM 1: columns are pairs (a,b), a outer
-//      acc0 (this thread's dP_0[a] so far) and p0a (P_0[a]) carry over when a group of VP columns straddles blocks
-template <int VP, int PHASE>
-__device__ __forceinline__ void epi1_block(uint32_t taddr, int j, const float (&P1)[VP], float (&dP1)[VP], float& acc0,
-                                           float& p0a, const float* e_row0, float* dp_row, bool valid) {
-  constexpr int OFF = (PHASE * 256) % VP;
-  const int gb = (j * 256) / VP;
+// ---- epilogue of one half (128 columns) of a block of GEMM 1: columns are pairs (a,b), a outer.  The eight epilogue
+//      warps form two sets; set H owns columns 128 H .. 128 H + 127 of every block and its own dP tile, so a group of VP
+//      columns cut by a range boundary is simply ADDED to the set's tile at the range end -- no carries, no races.
+template <int VP, int PHASE, int H>
+__device__ __forceinline__ void epi1_half(uint32_t taddr, int j, const float (&P1)[VP], float (&dP1)[VP],
+                                          const float* e_row0, float* dp_row, bool valid) {
+  constexpr int OFF = (PHASE * 256 + H * 128) % VP;
+  const int gb = (j * 256 + H * 128) / VP;
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f};   // four chains: one accumulator would serialise on the FMA latency
+  float p0a = 0.f;
+  if (OFF != 0) p0a = e_row0[(gb >> 2) * (kRS * 4) + (gb & 3)];
   uint32_t v[2][16];
   tmem_ld16(taddr, v[0]);
   tmem_wait_ld16(v[0]);
 #pragma unroll
-  for (int ch = 0; ch < 16; ++ch) {
-    if (ch + 1 < 16) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), v[(ch + 1) & 1]);
-    if (Cfg<VP>::NP % 256 == 0 || j * 256 + ch * 16 < Cfg<VP>::NP) {
+  for (int ch = 0; ch < 8; ++ch) {
+    if (ch + 1 < 8) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), v[(ch + 1) & 1]);
+    if (Cfg<VP>::NP % 128 == 0 || j * 256 + H * 128 + ch * 16 < Cfg<VP>::NP) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int rel = OFF + ch * 16 + i, idx = rel % VP, gr = rel / VP;
@@ -112,30 +172,32 @@ __device__ __forceinline__ void epi1_block(uint32_t taddr, int j, const float (&
           p0a = e_row0[(a >> 2) * (kRS * 4) + (a & 3)];
         }
         const float x = __uint_as_float(v[ch & 1][i]);
-        acc0 = fmaf(x, P1[idx], acc0);
+        acc0[i & 3] = fmaf(x, P1[idx], acc0[i & 3]);
         dP1[idx] = fmaf(x, p0a, dP1[idx]);
-        if (idx == VP - 1) {
-          dp_row[gb + gr] = valid ? acc0 : 0.f;
-          acc0 = 0.f;
+        if (idx == VP - 1 || (ch == 7 && i == 15)) {
+          if (valid) dp_row[gb + gr] += (acc0[0] + acc0[1]) + (acc0[2] + acc0[3]);
+          acc0[0] = acc0[1] = acc0[2] = acc0[3] = 0.f;
         }
       }
     }
-    if (ch + 1 < 16) tmem_wait_ld16(v[(ch + 1) & 1]);
+    if (ch + 1 < 8) tmem_wait_ld16(v[(ch + 1) & 1]);
   }
 }
 
-// ---- epilogue of one block of GEMM 2: columns are pairs (b,c), b outer; dP_2[c] += H[b,c] P_1[b]
-template <int VP, int PHASE>
-__device__ __forceinline__ void epi2_block(uint32_t taddr, int j, float (&dP2)[VP], float& p1b, const float* e_row1) {
-  constexpr int OFF = (PHASE * 256) % VP;
-  const int gb = (j * 256) / VP;
+// ---- the same for GEMM 2: columns are pairs (b,c), b outer; dP_2[c] += H[b,c] P_1[b]
+template <int VP, int PHASE, int H>
+__device__ __forceinline__ void epi2_half(uint32_t taddr, int j, float (&dP2)[VP], const float* e_row1) {
+  constexpr int OFF = (PHASE * 256 + H * 128) % VP;
+  const int gb = (j * 256 + H * 128) / VP;
+  float p1b = 0.f;
+  if (OFF != 0) p1b = e_row1[(gb >> 2) * (kRS * 4) + (gb & 3)];
   uint32_t v[2][16];
   tmem_ld16(taddr, v[0]);
   tmem_wait_ld16(v[0]);
 #pragma unroll
-  for (int ch = 0; ch < 16; ++ch) {
-    if (ch + 1 < 16) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), v[(ch + 1) & 1]);
-    if (Cfg<VP>::NP % 256 == 0 || j * 256 + ch * 16 < Cfg<VP>::NP) {
+  for (int ch = 0; ch < 8; ++ch) {
+    if (ch + 1 < 8) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), v[(ch + 1) & 1]);
+    if (Cfg<VP>::NP % 128 == 0 || j * 256 + H * 128 + ch * 16 < Cfg<VP>::NP) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int rel = OFF + ch * 16 + i, idx = rel % VP, gr = rel / VP;
@@ -146,69 +208,73 @@ __device__ __forceinline__ void epi2_block(uint32_t taddr, int j, float (&dP2)[V
         dP2[idx] = fmaf(__uint_as_float(v[ch & 1][i]), p1b, dP2[idx]);
       }
     }
-    if (ch + 1 < 16) tmem_wait_ld16(v[(ch + 1) & 1]);
+    if (ch + 1 < 8) tmem_wait_ld16(v[(ch + 1) & 1]);
   }
 }
 
 // the block's phase (where it starts inside a group of VP columns) is a runtime value with PH possible values: pick the
 // instantiation whose register indices are static
-template <int VP, int PHASE = 0>
+template <int VP, int H, int PHASE = 0>
 __device__ __forceinline__ void epi1_dispatch(int ph, uint32_t taddr, int j, const float (&P1)[VP], float (&dP1)[VP],
-                                              float& acc0, float& p0a, const float* e_row0, float* dp_row, bool valid) {
+                                              const float* e_row0, float* dp_row, bool valid) {
   if constexpr (PHASE + 1 < Cfg<VP>::PH) {
     if (ph != PHASE) {
-      epi1_dispatch<VP, PHASE + 1>(ph, taddr, j, P1, dP1, acc0, p0a, e_row0, dp_row, valid);
+      epi1_dispatch<VP, H, PHASE + 1>(ph, taddr, j, P1, dP1, e_row0, dp_row, valid);
       return;
     }
   }
-  epi1_block<VP, PHASE>(taddr, j, P1, dP1, acc0, p0a, e_row0, dp_row, valid);
+  epi1_half<VP, PHASE, H>(taddr, j, P1, dP1, e_row0, dp_row, valid);
 }
-template <int VP, int PHASE = 0>
-__device__ __forceinline__ void epi2_dispatch(int ph, uint32_t taddr, int j, float (&dP2)[VP], float& p1b,
-                                              const float* e_row1) {
+template <int VP, int H, int PHASE = 0>
+__device__ __forceinline__ void epi2_dispatch(int ph, uint32_t taddr, int j, float (&dP2)[VP], const float* e_row1) {
   if constexpr (PHASE + 1 < Cfg<VP>::PH) {
     if (ph != PHASE) {
-      epi2_dispatch<VP, PHASE + 1>(ph, taddr, j, dP2, p1b, e_row1);
+      epi2_dispatch<VP, H, PHASE + 1>(ph, taddr, j, dP2, e_row1);
       return;
     }
   }
-  epi2_block<VP, PHASE>(taddr, j, dP2, p1b, e_row1);
+  epi2_half<VP, PHASE, H>(taddr, j, dP2, e_row1);
 }
 
-template <int VP>
+template <int VP, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
-eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant__ BArgs a) {
+eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant__ CUtensorMap tp,
+                   const __grid_constant__ BArgs a) {
   using C = Cfg<VP>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) BBars bars;
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t issue_turn;   // number of blocks whose MMAs are all issued (leader CTA)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_p = smem_raw + (base - smem_u32(smem_raw));
-  // layout: [Ehi 0][Ehi 1][Elo 0][Elo 1][G stages][dP tile][valid flags 2 x 128]
+  // layout: [Ehi 0][Ehi 1][Elo 0][Elo 1][G stages][dP tile of set 0][dP tile of set 1][valid flags 2 x 128]
   const uint32_t ehi_u = base, elo_u = base + 2 * C::kPlane, stg_u = base + 4 * C::kPlane;
   float* ehi_p = reinterpret_cast<float*>(base_p);
   float* elo_p = reinterpret_cast<float*>(base_p + 2 * C::kPlane);
-  float* dpt = reinterpret_cast<float*>(base_p + 4 * C::kPlane + (size_t)C::NST * C::kStage);
-  uint8_t* vflag = reinterpret_cast<uint8_t*>(dpt + 128 * C::LDP);
+  float* dpt = reinterpret_cast<float*>(base_p + 4 * C::kPlane + (size_t)C::NST * C::kStage);   // [2 sets][128][LDP]
+  uint8_t* vflag = reinterpret_cast<uint8_t*>(dpt + 2 * 128 * C::LDP);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_tp = (a.n_tiles + 1) >> 1;
   const int my_tp = (n_tp - pair + n_pairs - 1) / n_pairs;
+  long long* prof = (PROF && a.prof) ? a.prof + (size_t)blockIdx.x * 16 : nullptr;
 
   if (warp == 1) tmem_alloc2(&tmem_slot, 512);
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) {
+    issue_turn = 0;
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&bars.full[s], 1);     // the leader's expect_tx arrival; bytes from both CTAs
       mbar_init(&bars.empty[s], 1);    // one multicast commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.d_full[s], 1);   // multicast commit
-      mbar_init(&bars.d_empty[s], 8);  // leader only: the epilogue warps of both CTAs
-      mbar_init(&bars.a_full[s], 8);   // leader only: the staging warps of both CTAs
-      mbar_init(&bars.a_ready[s], 4);  // local: staging warps -> epilogue warps
-      mbar_init(&bars.a_free[s], 5);   // local: multicast commit (MMAs done with the tile) + 4 epilogue warps
+      mbar_init(&bars.d_empty[s], 16); // leader only: the eight epilogue warps of both CTAs
+      mbar_init(&bars.a_full[s], 2);   // leader only: the staging warp of both CTAs
+      mbar_init(&bars.a_ready[s], 1);  // local: staging warp -> epilogue warps
+      mbar_init(&bars.a_free[s], 10);  // local: two multicast commits (each issuer's MMAs done with the tile) + 8 epilogue warps
+      mbar_init(&bars.p_full[s], 1);   // local: the TMA box of posterior rows has landed
     }
     fence_mbar_init();
   }
@@ -221,70 +287,126 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
     // ------------------------------------------------------------------ G image producer (one per CTA)
     if (lane == 0) {
       int it = 0;
-      const int per_tile = 2 * C::NB * C::KS;
+      const int per_tile = 2 * C::NB * C::SPB;
+      ProfTimer<PROF> tot{prof, 0}, tw{prof, 0};
+      tot.start();
       for (int i = 0; i < my_tp; ++i) {
         for (int u = 0; u < per_tile; ++u, ++it) {
           const int s = it % C::NST, use = it / C::NST;
+          tw.start();
           if (use > 0) mbar_wait(&bars.empty[s], (uint32_t)((use - 1) & 1));
+          tw.stop(kProfTmaEmpty);
+          if (a.dbg & 1) continue;
           if (rank == 0) mbar_expect_tx(&bars.full[s], 2 * C::kStage);
-          tma2_load_2d(stg_u + (uint32_t)s * C::kStage, &tg, 0, (u * 2 + (int)rank) * 64, &bars.full[s]);
+          tma2_load_2d(stg_u + (uint32_t)s * C::kStage, &tg, 0, (u * 2 + (int)rank) * 128, &bars.full[s]);
         }
       }
+      tot.stop(kProfTmaTotal);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers (leader CTA only)
+    // Two warps, one per TMEM bank: warp 1 issues the even blocks, warp 2 the odd ones.  One issuing thread needs ~40
+    // instructions per K-step (barrier poll, election, three UTCHMMA with their uniform-register operands, commit) at
+    // 5-6 clk per dependent instruction against the 384 clk the three MMAs take: a single issuer sets the pace
+    // (profiles/r02_tcbwd.md).  With two issuers each has 768 clk per K-step.  The whole warp walks the loop
+    // (waits are warp-wide, one elected lane issues); descriptors are a constant high word and a low word that advances
+    // by small constants.  Blocks go to different banks, so the order in which the two warps' MMAs reach the pipe is
+    // irrelevant; every commit covers the issuing thread's own MMAs.
+    if (rank == 0) {
+      const int p = warp - 1;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      int it = 0, blk = 0;
+      constexpr uint32_t kLboA = (uint32_t)(kRS * 16 >> 4) << 16, kLboB = (2048u >> 4) << 16;
+      constexpr uint32_t kAStep = (uint32_t)(2 * kRS * 16) >> 4;       // two 16-byte chunks per K-step
+      const uint32_t b_lo0 = ((stg_u >> 4) & 0x3fffu) | kLboB;
+      const uint32_t d = tmem + (uint32_t)(p * 256);
+      uint32_t blk = 0;
+      ProfTimer<PROF> tot{(lane == 0 && p == 0) ? prof : nullptr, 0}, tw{(lane == 0 && p == 0) ? prof : nullptr, 0};
+      tot.start();
       for (int i = 0; i < my_tp; ++i) {
         const int buf = i & 1;
+        tw.start();
         mbar_wait(&bars.a_full[buf], (uint32_t)((i >> 1) & 1));
+        tw.stop(kProfMmaAFull);
         tc_fence_after();
-        const uint32_t ah0 = ehi_u + (uint32_t)buf * C::kPlane, al0 = elo_u + (uint32_t)buf * C::kPlane;
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t shift = g == 0 ? 32u : 0u;   // GEMM 1 reads row w+2, GEMM 2 row w
-          for (int j = 0; j < C::NB; ++j, ++blk) {
-            const int bank = blk & 1;
-            if (blk >= 2) {
-              mbar_wait(&bars.d_empty[bank], (uint32_t)(((blk >> 1) - 1) & 1));
-              tc_fence_after();
-            }
-            const uint32_t d = tmem + (uint32_t)(bank * 256);
+        const uint32_t ah0 = (((ehi_u + (uint32_t)buf * C::kPlane) >> 4) & 0x3fffu) | kLboA;
+        const uint32_t al0 = (((elo_u + (uint32_t)buf * C::kPlane) >> 4) & 0x3fffu) | kLboA;
 #pragma unroll 1
-            for (int ks = 0; ks < C::KS; ++ks, ++it) {
-              const int s = it % C::NST, use = it / C::NST;
-              mbar_wait(&bars.full[s], (uint32_t)(use & 1));
-              tc_fence_after();
-              const uint32_t koff = (uint32_t)(2 * ks) * (kRS * 16u) + shift;
-              const uint64_t ah = smem_desc_kmajor(ah0 + koff, kRS * 16u, 128u);
-              const uint64_t al = smem_desc_kmajor(al0 + koff, kRS * 16u, 128u);
-              const uint32_t sb = stg_u + (uint32_t)s * C::kStage;
-              const uint64_t bh = smem_desc_kmajor(sb, 2048u, 128u), bl = smem_desc_kmajor(sb + 4096u, 2048u, 128u);
-              mma2_tf32_ss(d, ah, bh, idesc, ks ? 1u : 0u);
-              mma2_tf32_ss(d, al, bh, idesc, 1u);
-              mma2_tf32_ss(d, ah, bl, idesc, 1u);
+        for (int gj = 0; gj < 2 * C::NB; ++gj, ++blk) {
+          if ((blk & 1u) != (uint32_t)p) continue;
+          const uint32_t shift = gj < C::NB ? 2u : 0u;   // GEMM 1 reads row w+2, GEMM 2 row w (16 bytes per row)
+          if (lane == 0) trace<PROF>(a.prof, 0, blk);
+          if (blk >= 2) {
+            tw.start();
+            mbar_wait(&bars.d_empty[p], ((blk >> 1) - 1) & 1u);
+            tw.stop(kProfMmaDEmpty);
+            tc_fence_after();
+          }
+          if (lane == 0) trace<PROF>(a.prof, 1, blk);
+          // blocks are issued in order (the other warp's block first if it is older): the stage ring is consumed in
+          // order and a block's MMAs reach the pipe back to back
+          while (*(volatile uint32_t*)&issue_turn != blk) {}
+          const uint32_t it0 = blk * C::SPB;
+#pragma unroll
+          for (int st = 0; st < C::SPB; ++st) {
+            const uint32_t it = it0 + st, s = it % C::NST, use = it / C::NST;
+            tw.start();
+            if (!(a.dbg & 1)) mbar_wait(&bars.full[s], use & 1u);
+            tw.stop(kProfMmaFull);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t ks = 2 * st + kk;
+                const uint32_t ah = ah0 + shift + ks * kAStep, al = al0 + shift + ks * kAStep;
+                const uint32_t bh = b_lo0 + s * (C::kStage >> 4) + kk * (8192u >> 4), bl = bh + (4096u >> 4);
+                mma2_tf32_w(d, ah, bh, idesc, ks ? 1u : 0u);
+                mma2_tf32_w(d, al, bh, idesc, 1u);
+                mma2_tf32_w(d, ah, bl, idesc, 1u);
+              }
               mma2_commit_both(&bars.empty[s]);
             }
-            mma2_commit_both(&bars.d_full[bank]);
+            __syncwarp();
           }
+          if (elect_one()) {
+            mma2_commit_both(&bars.d_full[p]);
+            *(volatile uint32_t*)&issue_turn = blk + 1;
+          }
+          __syncwarp();
+          if (lane == 0) trace<PROF>(a.prof, 2, blk);
         }
-        mma2_commit_both(&bars.a_free[buf]);
+        if (elect_one()) mma2_commit_both(&bars.a_free[buf]);   // this warp's MMAs are done with the posterior tile
+        __syncwarp();
       }
+      tot.stop(kProfMmaTotal);
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: thread = TMEM lane = window
-    const int quarter = warp & 3, w = quarter * 32 + lane;
-    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    float* dp_row = dpt + w * C::LDP;
+    // Eight warps in two sets: set h (warps 4+4h .. 7+4h) reads columns 128 h .. 128 h + 127 of every block -- two warps
+    // per scheduler hide each other's TMEM-load latency, and a block is drained in half the time, which with only two
+    // accumulator banks is what keeps the tensor pipe fed (profiles/r02_tcbwd.md).
+    const int set = (warp - 4) >> 2, quarter = warp & 3, w = quarter * 32 + lane;
+    const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 128);
+    float* dpt_s = dpt + set * 128 * C::LDP;
+    float* dp_row = dpt_s + w * C::LDP;
+    auto set_bar = [&]() {
+      if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     int blk = 0;
+    ProfTimer<PROF> tot{tid == 128 ? prof : nullptr, 0}, tw{tid == 128 ? prof : nullptr, 0};
+    tot.start();
     for (int i = 0; i < my_tp; ++i) {
       const int buf = i & 1;
       const long long r0 = (long long)(2 * (pair + i * n_pairs) + (int)rank) * kTileRows - 2;
+      tw.start();
       mbar_wait(&bars.a_ready[buf], (uint32_t)((i >> 1) & 1));
+      tw.stop(kProfEpiAReady);
       const bool valid = vflag[buf * 128 + w] != 0;
       const float* e_tile = ehi_p + (size_t)buf * (C::kPlane / 4);
       const float* e_row0 = e_tile + w * 4;
       const float* e_row1 = e_tile + (w + 1) * 4;
+#pragma unroll
+      for (int k = 0; k < VP; ++k) dp_row[k] = 0.f;      // dP_0 partial sums are ADDED to this row
       {
         float P1[VP], dP1[VP];
 #pragma unroll
@@ -294,19 +416,26 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         }
 #pragma unroll
         for (int k = 0; k < VP; ++k) dP1[k] = 0.f;
-        float acc0 = 0.f, p0a = 0.f;
 #pragma unroll 1
         for (int j = 0; j < C::NB; ++j, ++blk) {
           const int bank = blk & 1;
+          tw.start();
           mbar_wait(&bars.d_full[bank], (uint32_t)((blk >> 1) & 1));
+          tw.stop(kProfEpiDFull);
+          if (tid == 128) trace<PROF>(a.prof, 3, (uint32_t)blk);
           tc_fence_after();
-          epi1_dispatch<VP>(j % C::PH, tmem + lane_field + (uint32_t)(bank * 256), j, P1, dP1, acc0, p0a, e_row0,
-                                   dp_row, valid);
+          tw.start();
+          if (!(a.dbg & 2)) {
+            if (set == 0) epi1_dispatch<VP, 0>(j % C::PH, tmem + lane_col + (uint32_t)(bank * 256), j, P1, dP1, e_row0, dp_row, valid);
+            else epi1_dispatch<VP, 1>(j % C::PH, tmem + lane_col + (uint32_t)(bank * 256), j, P1, dP1, e_row0, dp_row, valid);
+          }
+          tw.stop(kProfEpiWork);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&bars.d_empty[bank], 0);
+          if (lane == 0) mbar_arrive_cluster_light(&bars.d_empty[bank], 0);
+          if (tid == 128) trace<PROF>(a.prof, 4, (uint32_t)blk);
         }
-        named_bar_epi();   // every dP_0 row is in the tile before any dP_1 is added to it
+        set_bar();   // every dP_0 row of this set's tile is in before any dP_1 is added to it
         if (w + 1 < 128) {
 #pragma unroll
           for (int k = 0; k < VP; ++k) dp_row[C::LDP + k] += valid ? dP1[k] : 0.f;
@@ -316,18 +445,26 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         float dP2[VP];
 #pragma unroll
         for (int k = 0; k < VP; ++k) dP2[k] = 0.f;
-        float p1b = 0.f;
 #pragma unroll 1
         for (int j = 0; j < C::NB; ++j, ++blk) {
           const int bank = blk & 1;
+          tw.start();
           mbar_wait(&bars.d_full[bank], (uint32_t)((blk >> 1) & 1));
+          tw.stop(kProfEpiDFull);
+          if (tid == 128) trace<PROF>(a.prof, 3, (uint32_t)blk);
           tc_fence_after();
-          epi2_dispatch<VP>(j % C::PH, tmem + lane_field + (uint32_t)(bank * 256), j, dP2, p1b, e_row1);
+          tw.start();
+          if (!(a.dbg & 2)) {
+            if (set == 0) epi2_dispatch<VP, 0>(j % C::PH, tmem + lane_col + (uint32_t)(bank * 256), j, dP2, e_row1);
+            else epi2_dispatch<VP, 1>(j % C::PH, tmem + lane_col + (uint32_t)(bank * 256), j, dP2, e_row1);
+          }
+          tw.stop(kProfEpiWork);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&bars.d_empty[bank], 0);
+          if (lane == 0) mbar_arrive_cluster_light(&bars.d_empty[bank], 0);
+          if (tid == 128) trace<PROF>(a.prof, 4, (uint32_t)blk);
         }
-        named_bar_epi();   // dP_1 rows are in
+        set_bar();   // dP_1 rows are in
         if (w + 2 < 128) {
 #pragma unroll
           for (int k = 0; k < VP; ++k) dp_row[2 * C::LDP + k] += valid ? dP2[k] : 0.f;
@@ -336,50 +473,90 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
       // the posterior tile is no longer needed by this warp
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a_free[buf]);
-      named_bar_epi();
-      // rows 2..127 of the tile are complete: one coalesced write
+      asm volatile("bar.sync 3, 256;" ::: "memory");   // both sets' tiles are complete
+      // rows 2..127 are complete: one coalesced write of the sum of the two sets' tiles (index arithmetic on compile-time
+      // VP, eight independent elements in flight per thread)
       {
-        const int V = a.V, total = kTileRows * V, te = tid - 128;
-        for (int idx = te; idx < total; idx += 128) {
-          const int r = idx / V, v = idx - r * V;
-          const long long gr = r0 + 2 + r;
-          if (gr < a.NR) a.dpx[gr * V + v] = dpt[(r + 2) * C::LDP + v];
+        const int V = a.V, te = tid - 128;
+        constexpr int kTotal = kTileRows * VP;
+        float* out0 = a.dpx + (r0 + 2) * V;
+        const long long rows_left = a.NR - (r0 + 2);
+#pragma unroll 8
+        for (int idx = te; idx < kTotal; idx += 256) {
+          const int r = idx / VP, v = idx - r * VP;
+          const float x = dpt[(r + 2) * C::LDP + v] + dpt[(128 + r + 2) * C::LDP + v];
+          if (v < V && r < rows_left) out0[r * V + v] = x;
         }
       }
-      named_bar_epi();     // the tile is free for the next dP_0 rows
+      asm volatile("bar.sync 3, 256;" ::: "memory");   // the tiles are free for the next dP_0 rows
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ staging of posterior tiles
-    const int ts = tid - 256, V = a.V;
+    tot.stop(kProfEpiTotal);
+  }
+  if (warp == 3) {
+    // ------------------------------------------------------------------ staging of posterior tiles (one warp)
+    const int V = a.V;
+    ProfTimer<PROF> tot{lane == 0 ? prof : nullptr, 0}, tw{lane == 0 ? prof : nullptr, 0};
+    tot.start();
     for (int i = 0; i < my_tp; ++i) {
       const int buf = i & 1;
       const long long r0 = (long long)(2 * (pair + i * n_pairs) + (int)rank) * kTileRows - 2;
+      tw.start();
       if (i >= 2) mbar_wait(&bars.a_free[buf], (uint32_t)(((i >> 1) - 1) & 1));
+      tw.stop(kProfStgFree);
       float* eh = ehi_p + (size_t)buf * (C::kPlane / 4);
       float* el = elo_p + (size_t)buf * (C::kPlane / 4);
-      for (int idx = ts; idx < C::KQ * kRS; idx += 128) {
-        const int q = idx / kRS, r = idx - q * kRS;
-        const long long gr = r0 + r;
-        float e[4] = {0.f, 0.f, 0.f, 0.f};
-        if (gr >= 0 && gr < a.NR) {
-          const float* src = a.px + gr * V + 4 * q;
-          if ((V & 3) == 0 && 4 * q + 3 < V) {
-            const float4 p = __ldg(reinterpret_cast<const float4*>(src));
-            e[0] = p.x + kEpsB; e[1] = p.y + kEpsB; e[2] = p.z + kEpsB; e[3] = p.w + kEpsB;
-          } else {
+      if (a.px_tma) {
+        // one TMA box {4 floats, 130 rows, KQ chunks} of the [rows][V] posteriors lands as [chunk][row][4] -- the
+        // K-major core-matrix order the MMA reads -- with rows outside the batch and phones >= V zero-filled; then one
+        // pass over shared memory adds eps in place and writes the tf32 remainder plane
+        if (lane == 0) {
+          mbar_expect_tx(&bars.p_full[buf], C::kPlane);
+          tma_load_3d(ehi_u + (uint32_t)buf * C::kPlane, &tp, 0, (int)r0, 0, &bars.p_full[buf]);
+        }
+        mbar_wait(&bars.p_full[buf], (uint32_t)((i >> 1) & 1));
+        constexpr int kItems = C::KQ * kRS, kBatch = 8;
+#pragma unroll 1
+        for (int base_i = 0; base_i < kItems; base_i += 32 * kBatch) {
+          float4 p[kBatch];   // loads first, stores after: the compiler cannot reorder them itself (same arrays)
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int idx = base_i + u * 32 + lane;
+            if (idx < kItems) p[u] = *reinterpret_cast<const float4*>(eh + (size_t)idx * 4);
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int idx = base_i + u * 32 + lane;
+            if (idx < kItems) {
+              p[u].x += kEpsB; p[u].y += kEpsB; p[u].z += kEpsB; p[u].w += kEpsB;
+              *reinterpret_cast<float4*>(eh + (size_t)idx * 4) = p[u];
+              *reinterpret_cast<float4*>(el + (size_t)idx * 4) =
+                  make_float4(tf32_lo(p[u].x), tf32_lo(p[u].y), tf32_lo(p[u].z), tf32_lo(p[u].w));
+            }
+          }
+        }
+      } else {
+#pragma unroll 6
+        for (int idx = lane; idx < C::KQ * kRS; idx += 32) {
+          const int q = idx / kRS, r = idx - q * kRS;
+          const long long gr = r0 + r;
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          if (gr >= 0 && gr < a.NR) {
+            const float* src = a.px + gr * V + 4 * q;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (4 * q + k < V) e[k] = __ldg(src + k) + kEpsB;
           }
+          *reinterpret_cast<float4*>(eh + (size_t)idx * 4) = make_float4(e[0], e[1], e[2], e[3]);
+          *reinterpret_cast<float4*>(el + (size_t)idx * 4) = make_float4(tf32_lo(e[0]), tf32_lo(e[1]), tf32_lo(e[2]), tf32_lo(e[3]));
         }
-        *reinterpret_cast<float4*>(eh + (size_t)idx * 4) = make_float4(e[0], e[1], e[2], e[3]);
-        *reinterpret_cast<float4*>(el + (size_t)idx * 4) = make_float4(tf32_lo(e[0]), tf32_lo(e[1]), tf32_lo(e[2]), tf32_lo(e[3]));
       }
-      {
-        const long long gr = r0 + ts;   // window start row of TMEM lane ts
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ww = lane + 32 * k;
+        const long long gr = r0 + ww;   // window start row of TMEM lane ww
         bool ok = false;
         if (gr >= 0 && gr < a.NR) ok = __ldg(a.mask + gr) != 0 && (int)(gr % a.T) <= a.T - 3;
-        vflag[buf * 128 + ts] = ok ? 1 : 0;
+        vflag[buf * 128 + ww] = ok ? 1 : 0;
       }
       fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
@@ -388,6 +565,7 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         mbar_arrive_cluster(&bars.a_full[buf], 0);
       }
     }
+    tot.stop(kProfStgTotal);
   }
   tc_fence_before();
   cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal it or read its operands
@@ -402,32 +580,40 @@ __global__ void __launch_bounds__(256) eodm_tcb_image_kernel(const float* __rest
   if (i >= n) return;
   float g = 0.f;
   for (int z = zmap[i]; z >= 0; z = next_dup[z]) g += gS[z];   // duplicates of a trigram add up, in table order
-  // element i of the plane-less index -> (stage-and-rank, q, row, e); planes are 1024 floats apart inside 2048-float units
-  const long long unit = i >> 10, in = i & 1023;
-  img[unit * 2048 + in] = g;
-  img[unit * 2048 + 1024 + in] = tf32_lo(g);
+  // element i of the plane-less index -> (K-step, q, row, e); every K-step is 1024 entries here and 2048 floats (hi plane,
+  // lo plane) in the image
+  const long long kstep = i >> 10, in = i & 1023;
+  img[kstep * 2048 + in] = g;
+  img[kstep * 2048 + 1024 + in] = tf32_lo(g);
 }
 
-template <int VP>
-cudaError_t launch_vp(const CUtensorMap& tg, const BArgs& a, int sm_count, cudaStream_t st) {
-  auto k = eodm_tc_bwd_kernel<VP>;
+template <int VP, bool PROF = false>
+cudaError_t launch_vp(const CUtensorMap& tg, const CUtensorMap& tp, const BArgs& a, int sm_count, cudaStream_t st) {
+  auto k = eodm_tc_bwd_kernel<VP, PROF>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<VP>::kSmem);
   if (e != cudaSuccess) return e;
   const int n_tp = (a.n_tiles + 1) / 2;
   const int pairs = n_tp < sm_count / 2 ? n_tp : sm_count / 2;
-  k<<<2 * pairs, kThreadsB, Cfg<VP>::kSmem, st>>>(tg, a);
+  k<<<2 * pairs, kThreadsB, Cfg<VP>::kSmem, st>>>(tg, tp, a);
   return cudaGetLastError();
 }
 
+long long* g_tcb_prof = nullptr;
+int g_tcb_dbg = 0;
+
 }  // namespace
+
+// Test hook, not part of the public header: a device buffer of 16 x int64 per CTA that the VJP kernel's roles add their
+// waiting / working cycles to (tools/tcb_profile.py); nullptr switches it off.
+extern "C" void eodm_debug_tcb_profile(long long* dev_buf) { g_tcb_prof = dev_buf; }
+extern "C" void eodm_debug_tcb_switches(int dbg) { g_tcb_dbg = dbg; }
 
 int eodm_tcb_vp(int n, int V, bool full_order) {
   if (n != 3 || !full_order || V < 2) return 0;
   if (V <= 16) return 16;
   if (V <= 32) return 32;
   if (V <= 48) return 48;
-  if (V <= 64) return 64;
-  return 0;
+  return 0;   // V = 64 would need 133 KB of posterior planes + two dP tiles: over the 227 KB of one CTA
 }
 
 bool eodm_tcb_supported(const eodm_table* t) { return t->tcb.vp > 0 && t->tcb.d_zmap != nullptr; }
@@ -440,7 +626,7 @@ size_t eodm_tcb_workspace_bytes(const eodm_table* t) {
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
                     void* ws, cudaStream_t st) {
   if (!eodm_tcb_supported(t)) {
-    eodm_set_error("tensor-core VJP needs a trigram-only table over V <= 64");
+    eodm_set_error("tensor-core VJP needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
   }
   const long long NR = (long long)B * T;
@@ -461,7 +647,7 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   {
     const cuuint64_t dims[2] = {32u, (cuuint64_t)(n * 2 / 32)};
     const cuuint64_t strides[1] = {128u};
-    const cuuint32_t box[2] = {32u, 64u};
+    const cuuint32_t box[2] = {32u, 128u};
     const cuuint32_t estr[2] = {1u, 1u};
     if (fn(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
@@ -469,13 +655,33 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
       return EODM_ECUDA;
     }
   }
+  // the posteriors as [chunk of 4 phones][row][4 floats]: dims {4, NR, V/4}, strides {V*4 bytes, 16 bytes}
+  CUtensorMap tp;
+  const int vp = t->tcb.vp;
+  const bool px_tma = (t->V & 3) == 0 && (((uintptr_t)px) & 15) == 0;
+  if (px_tma) {
+    const cuuint64_t dims[3] = {4u, (cuuint64_t)NR, (cuuint64_t)(t->V / 4)};
+    const cuuint64_t strides[2] = {(cuuint64_t)t->V * 4u, 16u};
+    const cuuint32_t box[3] = {4u, (cuuint32_t)kRS, (cuuint32_t)(vp / 4)};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (fn(&tp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(px), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      eodm_set_error("cuTensorMapEncodeTiled failed for the posterior tile");
+      return EODM_ECUDA;
+    }
+  } else {
+    tp = tg;   // unused
+  }
   BArgs a;
   a.px = px;
+  a.px_tma = px_tma ? 1 : 0;
   a.mask = mask;
   a.dpx = dpx;
   a.NR = NR;
   a.T = T;
   a.V = t->V;
+  a.prof = g_tcb_prof;
+  a.dbg = g_tcb_dbg;
   const long long n_tiles = (NR + kTileRows - 1) / kTileRows;
   if (n_tiles > 0x7fffffffLL) {
     eodm_set_error("too many rows");
@@ -483,10 +689,9 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   }
   a.n_tiles = (int)n_tiles;
   switch (t->tcb.vp) {
-    case 16: e = launch_vp<16>(tg, a, t->sm_count, st); break;
-    case 32: e = launch_vp<32>(tg, a, t->sm_count, st); break;
-    case 48: e = launch_vp<48>(tg, a, t->sm_count, st); break;
-    default: e = launch_vp<64>(tg, a, t->sm_count, st); break;
+    case 16: e = launch_vp<16>(tg, tp, a, t->sm_count, st); break;
+    case 32: e = launch_vp<32>(tg, tp, a, t->sm_count, st); break;
+    default: e = a.prof ? launch_vp<48, true>(tg, tp, a, t->sm_count, st) : launch_vp<48>(tg, tp, a, t->sm_count, st); break;
   }
   if (e != cudaSuccess) {
     eodm_set_error("eodm_tc_bwd_kernel launch failed: %s", cudaGetErrorString(e));
