@@ -32,7 +32,26 @@ for p in (ROOT, os.path.join(ROOT, "unsupervised-asr_b200")):
 import numpy as np  # noqa: E402
 
 L2_FLUSH_BYTES = 256 << 20
-CPU_SAMPLE_B = 64
+CPU_CHUNK_B = 64          # the dense [B, T', K] intermediate of the reference graph is 1 GB per 64 utterances at timit_c2
+
+
+def load_synth():
+    """The synthetic-workload module WITHOUT importing the package (whose __init__ loads libeodm_b200.so): the
+    reference arm must not map the product library."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "eodm_synth_standalone", os.path.join(ROOT, "unsupervised-asr_b200", "eodm_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def config_of(w, name, world):
+    """The workload description both arms print: identical keys and values for the same workload."""
+    return {"workload": name, "B_per_gpu": w["B"], "T": w["T"], "V": w["V"], "n": w["n"], "K": w["K"],
+            "frames_per_step": int(w["mask"].sum()) * world,
+            "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
+            "parallelism": "batch-sharded x%d" % world}
 
 
 def parse():
@@ -47,6 +66,8 @@ def parse():
                          "(csrc/peer.cu), or ncclAllReduce followed by the loss kernel; auto = peer from 4 GPUs up "
                          "(measured: NCCL is 10 us ahead at N=2, the peer kernel 4 us ahead at N=8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the strong-scaling section (BASELINE configs[2]: V=72, orders 1-5, global batch 2048)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -56,35 +77,40 @@ def parse():
 # reduce -> loss, backward by autodiff) restated op for op on torch-CPU.  TensorFlow is not
 # installable in this image, so this is kind="port" (oracle/eodm_oracle.py:eodm_loss_literal).
 # ---------------------------------------------------------------------------
-def cpu_reference(w, steps, warmup, sample_b=CPU_SAMPLE_B):
+def cpu_reference(w, steps, warmup, sample_b=None):
+    """Times the reference formulation.  sample_b=None: the WHOLE batch per step, evaluated chunk by chunk
+    (CPU_CHUNK_B utterances at a time -- the graph materialises [B, T', K] several times over); otherwise the first
+    sample_b utterances only (the bounded `cpu_baseline` leg of the default run)."""
     import torch
 
     from oracle import eodm_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = min(sample_b, w["B"])
-    logits, mask = w["logits"][:Bs], w["mask"][:Bs]
+    Bs = w["B"] if sample_b is None else min(sample_b, w["B"])
     kernel = O.ids_to_kernel(w["ids"], w["V"])
-    frames = int(mask.sum())
+    chunks = [(b0, min(Bs, b0 + CPU_CHUNK_B)) for b0 in range(0, Bs, CPU_CHUNK_B)]
+    frames = int(w["mask"][:Bs].sum())
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.eodm_loss_literal(logits, mask, kernel, w["py"], dtype="float32", need_grad=True)
+        for b0, b1 in chunks:
+            O.eodm_loss_literal(w["logits"][b0:b1], w["mask"][b0:b1], kernel, w["py"], dtype="float32", need_grad=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+    what = ("all %d utterances of the %s batch, %d at a time" % (Bs, w["name"], CPU_CHUNK_B) if sample_b is None else
+            "first %d of %d utterances of the %s batch" % (Bs, w["B"], w["name"]))
     return dict(frames=frames, times=times, cores=cores, sample_b=Bs,
-                sample="first %d of %d utterances of the %s batch (T=%d, V=%d, n=%d, K=%d), fp32, fwd+bwd by autograd; "
-                       "TF-equivalent dense restatement on torch-CPU (TF 2.x not installable in this image)"
-                       % (Bs, w["B"], w["name"], w["T"], w["V"], w["n"], w["K"]))
+                sample="%s (T=%d, V=%d, n=%d, K=%d), fp32, fwd+bwd by autograd; TF-equivalent dense restatement on "
+                       "torch-CPU (TF 2.x not installable in this image)" % (what, w["T"], w["V"], w["n"], w["K"]))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from eodm_b200 import synth
+    synth = load_synth()
     w = synth.workload(args.workload)
     w["name"] = args.workload
     r = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
@@ -94,8 +120,7 @@ def run_reference(args):
         "impl": "reference", "metric": "EODM fwd+bwd frames/sec", "value": val, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "B": w["B"], "T": w["T"], "V": w["V"], "n": w["n"], "K": w["K"],
-                   "step": "bounded sample: %d utterances per step" % r["sample_b"]},
+        "config": config_of(w, args.workload, max(1, args.gpus)),
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,6 +274,36 @@ def main():
     value = frames_all / (ms_per_step * 1e-3)
     t_clk0 = t0
 
+    # ---- N > 1: the same N batches on ONE GPU (rank 0), compared with what the ranks computed together ----
+    parity = None
+    if world > 1:
+        step()
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(dlogits_d) for _ in range(world)] if rank == 0 else None
+        td.gather(dlogits_d, gathered, dst=0)
+        losses = [torch.empty_like(loss_d) for _ in range(world)] if rank == 0 else None
+        td.gather(loss_d, losses, dst=0)
+        if rank == 0:
+            ws_all = [synth.workload(args.workload, rank=r) for r in range(world)]
+            lg_all = torch.tensor(np.concatenate([x["logits"] for x in ws_all]), device=dev)
+            mk_all = torch.tensor(np.concatenate([x["mask"] for x in ws_all]), device=dev).to(torch.uint8)
+            one = E.Session(table, w["py"], B * world, T)
+            l1 = torch.zeros(1, device=dev)
+            d1 = torch.empty_like(lg_all)
+            one.step_device(lg_all.data_ptr(), mk_all.data_ptr(), B * world, T, l1.data_ptr(), d1.data_ptr(), stream)
+            torch.cuda.synchronize()
+            dN = torch.cat(gathered)
+            parity = {"what": "loss and dloss/d_logits of the %d sharded batches vs the same %d utterances as one batch on "
+                              "rank 0's GPU" % (world, B * world),
+                      "loss_rel": abs(float(loss_d) - float(l1)) / abs(float(l1)),
+                      "loss_spread_over_ranks": float(max(abs(float(x) - float(loss_d)) for x in losses)),
+                      "grad_max_rel": float((dN - d1).abs().max() / d1.abs().max()), "gate": 1e-6}
+            parity["ok"] = bool(parity["loss_rel"] <= 1e-6 and parity["grad_max_rel"] <= 1e-6
+                                and parity["loss_spread_over_ranks"] == 0.0)
+            one.close()
+            del lg_all, mk_all, d1, dN, gathered
+        barrier()
+
     # ---- the two counts kernels alone (rank-local; roofline of the dominant one) ----
     px = E.softmax_fwd(logits_d)
     counts = torch.empty(K + 1, device=dev)
@@ -274,14 +329,17 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     dom_is_bwd = t_b >= t_f
     ach = (fl_b / t_b if dom_is_bwd else fl_f / t_f) / 1e12
+    bwd_kernel = "eodm_tc_bwd_kernel" if E.uses_tensor_vjp(table) else "eodm_counts_bwd_kernel"
     roofline = {
-        "kernel": "eodm_counts_bwd_kernel" if dom_is_bwd else "eodm_counts_fwd_kernel",
+        "kernel": bwd_kernel if dom_is_bwd else "eodm_counts_fwd_kernel",
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
         "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s); CUDA-core FMA peak, not a tensor or HBM figure"
                        % ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "fallback 1965 MHz"),
         "traffic": None,
-        "fwd": {"ms": t_f * 1e3, "flops": fl_f, "tflops": fl_f / t_f / 1e12},
-        "bwd": {"ms": t_b * 1e3, "flops": fl_b, "tflops": fl_b / t_b / 1e12},
+        "fwd": {"kernel": "eodm_counts_fwd_kernel", "ms": t_f * 1e3, "flops": fl_f, "tflops": fl_f / t_f / 1e12,
+                "frac": fl_f / t_f / 1e12 / fp32_peak},
+        "bwd": {"kernel": bwd_kernel, "ms": t_b * 1e3, "flops": fl_b, "tflops": fl_b / t_b / 1e12,
+                "frac": fl_b / t_b / 1e12 / fp32_peak},
         "path_fwd_bwd": {"ms": (t_f + t_b) * 1e3, "roofline_ms": max((fl_f + fl_b) / (fp32_peak * 1e12),
                                                                     12.0 * B * T * V / (hbm_peak * 1e9)) * 1e3},
         "hbm": {"algorithmic_bytes": 12.0 * B * T * V, "peak_gbs": hbm_peak,
@@ -289,7 +347,7 @@ def main():
     }
     roofline["path_fwd_bwd"]["frac"] = roofline["path_fwd_bwd"]["roofline_ms"] / roofline["path_fwd_bwd"]["ms"]
     try:  # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if args.workload == "timit_c2":
             roofline["traffic"] = traffic.get(roofline["kernel"])
     except Exception:
@@ -301,8 +359,21 @@ def main():
     lds_peak = 0.90 * n_sm * sm_max * 1e6
     roofline["smem_wavefronts"] = {
         "fwd": {"algorithmic": wf_f, "floor_ms": wf_f / lds_peak * 1e3, "frac": wf_f / lds_peak / t_f},
-        "bwd": {"algorithmic": wf_b, "floor_ms": wf_b / lds_peak * 1e3, "frac": wf_b / lds_peak / t_b},
-        "peak_wavefronts_per_clk_per_sm": 0.90, "note": "measured LDS.32 rate; the walk's binding resource"}
+        "peak_wavefronts_per_clk_per_sm": 0.90, "note": "measured LDS.32 rate; the resource that binds the trie walk"}
+    if E.uses_tensor_vjp(table):
+        # the tensor-core VJP issues 2 GEMMs x ceil(VP^2/256) blocks x VP/8 K-steps x 3 (3xTF32) MMAs of 256x256x8 per pair
+        # of 126-row tiles; 128 clk each on a CTA pair (tools/ubench_mma2.cu)
+        vp = 16 if V <= 16 else 32 if V <= 32 else 48
+        mmas = 2 * ((vp * vp + 255) // 256) * (vp // 8) * 3
+        tile_pairs = ((B * T + 125) // 126 + 1) // 2
+        rounds = (tile_pairs + n_sm // 2 - 1) // (n_sm // 2)
+        floor_ms = rounds * mmas * 128 / (sm_max * 1e6) * 1e3
+        roofline["tensor_pipe"] = {"bwd": {"mma_per_tile_pair": mmas, "tile_pairs": tile_pairs, "rounds": rounds,
+                                           "floor_ms": floor_ms, "frac": floor_ms / (t_b * 1e3)},
+                                   "note": "128 clk per cta_group::2 tf32 MMA at sm_max_mhz; the resource that binds the VJP"}
+    else:
+        roofline["smem_wavefronts"]["bwd"] = {"algorithmic": wf_b, "floor_ms": wf_b / lds_peak * 1e3,
+                                              "frac": wf_b / lds_peak / t_b}
 
     # ---- end to end through the host-buffer session (H2D + D2H inside the timed region) ----
     e2e = None
@@ -351,6 +422,60 @@ def main():
         e2e["pipelined"] = {"value": frames_all / p_sec, "unit": "frames/s", "ms_per_step": p_sec * 1e3,
                             "loss": float(bufs[(args.steps - 1) & 1][3].array[0]),
                             "api": "eodm_session_submit / eodm_session_wait, two steps in flight; same copies per step"}
+    # ---- strong scaling: BASELINE configs[2] (V=72, one table per order 1-5, GLOBAL batch 2048 split over the ranks) ----
+    strong = None
+    if not args.no_strong:
+        c3 = synth.LIBRI_C3
+        if c3["B"] % world == 0:
+            tabs = synth.order_tables(c3["V"], c3["orders"])
+            ops3 = [E.NgramTable.from_ids(ids, c3["V"], device=local) for ids, _ in tabs]
+            lg3, mk3 = synth.libri_c3_shard(rank, world)
+            Bl = lg3.shape[0]
+            ms3 = E.MultiOrderSession(ops3, [py_ for _, py_ in tabs], Bl, c3["T"])
+            lg3_d = torch.tensor(lg3, device=dev)
+            mk3_d = torch.tensor(mk3, device=dev).to(torch.uint8)
+            loss3 = torch.zeros(len(tabs) + 1, device=dev)
+            dl3 = torch.empty_like(lg3_d)
+
+            def step3():
+                ms3.step_device(lg3_d.data_ptr(), mk3_d.data_ptr(), Bl, c3["T"], loss3.data_ptr(), dl3.data_ptr(), stream,
+                                comm=comm)
+
+            n3 = max(3, min(args.steps, 10))
+            t3, _, _ = timed(step3, n3, 3)
+            ms3_step = max_over_ranks(sum(t3)) / n3
+            fr3 = torch.tensor([float(mk3.sum())], dtype=torch.float64, device=dev)
+            if world > 1:
+                td.all_reduce(fr3)
+            strong = {"workload": "libri_c3", "scaling": "strong", "global_batch": c3["B"], "B_per_gpu": Bl, "T": c3["T"],
+                      "V": c3["V"], "orders": [list(o) for o in c3["orders"]], "frames_per_step": int(fr3[0]),
+                      "steps": n3, "ms_per_step": ms3_step, "value": float(fr3[0]) / (ms3_step * 1e-3), "unit": "frames/s",
+                      "loss": float(loss3[len(tabs)].item()),
+                      "step": "one fused multi-order step (eodm_multi_step_device): one softmax, five counts, ONE "
+                              "all-reduce of the packed [S_1, N, ..., S_5, N] buffer, one loss kernel, five VJPs into one "
+                              "dpx, one softmax VJP"}
+            if world > 1:
+                # the same global batch on rank 0's GPU alone
+                dl_all = [torch.empty_like(dl3) for _ in range(world)] if rank == 0 else None
+                td.gather(dl3, dl_all, dst=0)
+                if rank == 0:
+                    lgA, mkA = synth.libri_c3_shard(0, 1)
+                    one = E.MultiOrderSession(ops3, [py_ for _, py_ in tabs], c3["B"], c3["T"])
+                    lgA_d = torch.tensor(lgA, device=dev)
+                    mkA_d = torch.tensor(mkA, device=dev).to(torch.uint8)
+                    l1 = torch.zeros(len(tabs) + 1, device=dev)
+                    d1 = torch.empty_like(lgA_d)
+                    one.step_device(lgA_d.data_ptr(), mkA_d.data_ptr(), c3["B"], c3["T"], l1.data_ptr(), d1.data_ptr(), stream)
+                    torch.cuda.synchronize()
+                    dN = torch.cat(dl_all)
+                    strong["parity"] = {"loss_rel": abs(float(loss3[len(tabs)]) - float(l1[len(tabs)])) / abs(float(l1[len(tabs)])),
+                                        "grad_max_rel": float((dN - d1).abs().max() / d1.abs().max()), "gate": 1e-6}
+                    strong["parity"]["ok"] = bool(strong["parity"]["loss_rel"] <= 1e-6 and strong["parity"]["grad_max_rel"] <= 1e-6)
+                    one.close()
+                    del lgA_d, mkA_d, d1, dN, dl_all
+                barrier()
+            ms3.close()
+
     if rank == 0:
         clocks = sampler.summary(t_clk0, time.perf_counter())   # every timed region of this run
         sampler.stop()
@@ -359,26 +484,32 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(w, 3, 1)
+        r = cpu_reference(w, 3, 1, sample_b=CPU_CHUNK_B)
         best = min(r["times"])
         cpu = {"value": r["frames"] / best, "unit": "frames/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"] + "; 1 warm-up + best of 3 (%.2f s)" % best}
 
     if rank == 0:
-        launches_per_step = 7       # softmax, counts fwd, finish, loss, prepare_g, counts bwd, softmax VJP
+        # softmax, counts fwd, finish, loss (or the fused exchange+loss), G image (or prepare_g), VJP, softmax VJP
+        launches_per_step = 7
         out = {
             "metric": "EODM fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "B_per_gpu": B, "T": T, "V": V, "n": n, "K": K,
-                       "frames_per_step": frames_all, "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
-                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": "batch-sharded x%d" % world,
-                       "exchange": None if world == 1 else
-                       ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
-                       "path": "cuda-core trie walk (shared-memory operand tile, flat tails, node stream two entries ahead)"},
+            "config": config_of(w, args.workload, world),
+            "notes": {"l2": "flushed between timed steps (256 MiB write)",
+                      "exchange": None if world == 1 else
+                      ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
+                      "path": ("forward: cuda-core trie walk (shared-memory operand tile); VJP: tcgen05 cta_group::2 3xTF32, "
+                               "windows on the M axis, TMA-staged posterior tile" if E.uses_tensor_vjp(table) else
+                               "cuda-core trie walk (shared-memory operand tile, flat tails, node stream two entries ahead)")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),
         }
+        if parity is not None:
+            out["parity"] = parity
+        if strong is not None:
+            out["strong_scaling"] = strong
         _emit(json.dumps(out))
     if world > 1:
         if group is not None:

@@ -95,6 +95,13 @@ int eodm_counts_partial(const eodm_table* t, const float* px, const uint8_t* mas
  * (main_EODM.py:168 through EODM.py:18-20).  dpx f32[B][T][V] is overwritten. */
 int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
                     const float* gS, float* dpx, void* ws, void* stream);
+/* The same, ADDED to dpx: the gradient of one more table over the same posterior sequence (the tape of
+ * main_EODM.py:168 sums the gradients of every loss term that reads px). */
+int eodm_counts_bwd_acc(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                        const float* gS, float* dpx, void* ws, void* stream);
+/* 1 if eodm_counts_bwd serves this table on the tensor cores (tcgen05; trigram-only tables over V <= 48 that are dense
+ * enough), 0 if on the CUDA-core trie walk.  Informational. */
+int eodm_table_uses_tensor_vjp(const eodm_table* t);
 
 /* loss = -sum_z py[z]*log(S[z]/N + eps);  gS[z] = dloss/dS[z]   (models/EODM.py:20-23)
  * loss f32[1], gS f32[K] (gS may be NULL). */
@@ -176,6 +183,9 @@ int eodm_peer_loss(eodm_peer* p, const float* counts, const float* py, float eps
                    float* counts_out, void* stream);
 /* 1 if an earlier eodm_peer_loss gave up waiting (~10 s) for a peer and wrote NaN; synchronises the device. */
 int eodm_peer_failed(eodm_peer* p);
+/* How long eodm_peer_loss waits for a late peer before giving up (then loss, gS and counts_out are all NaN, so the
+ * failure cannot pass unnoticed into a later gradient all-reduce); seconds <= 0 waits for ever.  Default ~2 minutes. */
+int eodm_peer_set_timeout(eodm_peer* p, double seconds);
 
 /* ---- one-call step with HOST buffers (what a plugin user times end to end) ---- */
 /* Owns device buffers, pinned staging and a stream for batches up to [maxB, maxT]. */
@@ -192,6 +202,20 @@ int eodm_session_set_peer(eodm_session* s, eodm_peer* peer);
  * f32[B][T][V] (NULL = forward only) are device pointers. */
 int eodm_session_step_device(eodm_session* s, const float* logits, const uint8_t* mask, int B, int T, void* comm,
                              float* loss, float* dlogits, void* stream);
+/* ---- several tables over ONE posterior sequence --------------------------------------------------------------
+ * One P_Ngram per order (kernel_size = order), every one applied to the same `_logits` (the reference builds its table
+ * per run at main_EODM.py:56-61 and applies it at :164; SURVEY.md 8d config 3 runs orders 1-5 as five tables).  A step
+ * runs softmax ONCE, the counts of every table, ONE exchange of the packed [S_1, N, S_2, N, ...] buffer (`comm` as in
+ * eodm_allreduce_counts, NULL on one GPU), one loss kernel, every table's VJP into ONE dpx, and the softmax VJP once.
+ * loss_out f32[n_tables + 1] (device): weights[o] * loss_o, then their sum; dlogits f32[B][T][V] (NULL = forward only)
+ * is the gradient of that sum.  weights NULL = all 1.  At most 8 tables, same V and device. */
+typedef struct eodm_multi eodm_multi;
+int eodm_multi_create(const eodm_table* const* tables, const float* const* py_host, const float* weights, int n_tables,
+                      int maxB, int maxT, eodm_multi** out);
+void eodm_multi_destroy(eodm_multi* m);
+int eodm_multi_step_device(eodm_multi* m, const float* logits, const uint8_t* mask, int B, int T, void* comm,
+                           float* loss_out, float* dlogits, void* stream);
+
 /* Page-locked host memory for callers with no CUDA binding of their own. */
 int eodm_host_alloc(size_t bytes, void** out);
 int eodm_host_free(void* p);

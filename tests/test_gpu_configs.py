@@ -65,6 +65,57 @@ def test_libri_c3_five_orders(eodm):
         (rel_max(grad, ref["dlogits"]), rel_l2(grad, ref["dlogits"]))
 
 
+def _multi_loss_grad(eodm, tables, V, logits, mask, weights=None):
+    dev = torch.device("cuda:0")
+    ops = [eodm.PNgram(eodm.NgramTable.from_ids(ids, V, device=0)) for ids, _ in tables]
+    sess = eodm.MultiOrderSession(ops, [py for _, py in tables], logits.shape[0], logits.shape[1], weights=weights)
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    total, per = eodm.EODM_loss_multi(lg, torch.tensor(mask, device=dev), sess)
+    total.backward()
+    return float(total), per.cpu().numpy(), lg.grad.cpu().numpy(), sess
+
+
+def test_libri_c3_fused_multi_order_step(eodm):
+    """The five tables of BASELINE configs[2] as ONE step (eodm_multi_*: one softmax, packed counts, one loss kernel, every
+    VJP added into one dpx, one softmax VJP) against the oracle and against the five separate EODM_loss calls."""
+    c = eodm.synth.LIBRI_C3
+    tables = eodm.synth.order_tables(c["V"], c["orders"])
+    logits, mask = eodm.synth.libri_c3_shard(0, 8)                      # one rank's share at 8 GPUs: 256 utterances
+    ref = F.multi_order_loss_direct(logits, mask, tables)
+    total, per, grad, sess = _multi_loss_grad(eodm, tables, c["V"], logits, mask)
+    assert abs(total - ref["loss"]) <= TOL * abs(ref["loss"])
+    for got, want in zip(per[:5], ref["losses"]):
+        assert abs(got - want) <= TOL * abs(want)
+    assert abs(per[5] - total) == 0
+    assert rel_max(grad, ref["dlogits"]) <= TOL and rel_l2(grad, ref["dlogits"]) <= TOL
+    losses, grad5, _ = _gpu_loss_grad(eodm, tables, c["V"], logits, mask)
+    assert np.abs(np.array(losses) - per[:5]).max() <= 1e-6 * max(losses)
+    assert rel_max(grad, grad5.astype(np.float64)) <= 2e-6
+    # weights scale the terms and their gradients
+    w = np.array([0.5, 1.0, 2.0, 0.25, 1.5], np.float32)
+    total_w, per_w, grad_w, _ = _multi_loss_grad(eodm, tables, c["V"], logits[:40], mask[:40], weights=w)
+    ref_w = F.multi_order_loss_direct(logits[:40], mask[:40], tables, weights=w)
+    assert abs(total_w - ref_w["loss"]) <= TOL * abs(ref_w["loss"])
+    assert rel_max(grad_w, ref_w["dlogits"]) <= TOL
+    sess.close()
+
+
+def test_fused_step_mixes_tensor_core_and_walk_tables(eodm):
+    """A dense trigram table (tcgen05 VJP, accumulate mode) next to a unigram and a bigram table (trie walk) over V=48: the
+    three gradients land in one dpx."""
+    c = eodm.synth.STRESS_C5
+    tables = eodm.synth.order_tables(c["V"], c["orders"])
+    logits, mask = eodm.synth.batch(37, 211, c["V"], seed=3, len_lo=2)
+    ref = F.multi_order_loss_direct(logits, mask, tables)
+    total, per, grad, sess = _multi_loss_grad(eodm, tables, c["V"], logits, mask)
+    assert eodm.uses_tensor_vjp(sess.tables[2]) and not eodm.uses_tensor_vjp(sess.tables[1])
+    assert abs(total - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_max(grad, ref["dlogits"]) <= TOL and rel_l2(grad, ref["dlogits"]) <= TOL
+    with pytest.raises(eodm.EodmError):
+        eodm.EODM_loss_multi(torch.zeros(38, 211, 48, device="cuda:0"), torch.ones(38, 211, device="cuda:0"), sess)
+    sess.close()
+
+
 def test_stress_c5_long_ragged(eodm):
     """BASELINE configs[4]: V=48, orders 1-3 (K = 47 / 2048 / 10000), T = 4000, lengths log-uniform in [50, 4000] and rows
     shorter than the kernel (0, 1, 2 frames): tiles much shorter than an utterance, padding tiles skipped."""

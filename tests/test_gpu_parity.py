@@ -215,6 +215,27 @@ def test_eodm_loss_end_to_end_vs_oracle(eodm, seed, V, n, K, B, T, mixed, dup):
     assert rel_max(grad, r["dlogits"]) <= TOL and rel_l2(grad, r["dlogits"]) <= TOL
 
 
+def test_non_contiguous_and_half_precision_logits_train(eodm):
+    """EODM_loss on a sliced (non-contiguous) view and on fp16 logits: the converted copy made inside the autograd function
+    must not switch the gradient off (round-1 advisor finding)."""
+    ids, py, logits, mask = _random_case(51, 20, 3, 300, 4, 40, False)
+    dev = _dev()
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, 20, device=0))
+    ref = O.eodm_loss_direct(logits[:, :30], mask[:, :30], ids, 3, py)
+    full = torch.tensor(logits, device=dev, requires_grad=True)
+    loss = eodm.EODM_loss(full[:, :30], torch.tensor(mask[:, :30], device=dev), conv_op, 300, py)
+    loss.backward()
+    assert abs(float(loss) - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_max(full.grad[:, :30].cpu().numpy(), ref["dlogits"]) <= TOL and not full.grad[:, 30:].any()
+    half = torch.tensor(logits[:, :30], device=dev).half().requires_grad_(True)
+    loss = eodm.EODM_loss(half, torch.tensor(mask[:, :30], device=dev), conv_op, 300, py)
+    loss.backward()
+    assert half.grad is not None and half.grad.dtype == torch.float16
+    ref16 = O.eodm_loss_direct(half.detach().float().cpu().numpy(), mask[:, :30], ids, 3, py)
+    assert abs(float(loss) - ref16["loss"]) <= TOL * abs(ref16["loss"])
+    assert rel_max(half.grad.float().cpu().numpy(), ref16["dlogits"]) <= 2e-3          # fp16 storage of the gradient
+
+
 def test_peaky_posteriors(eodm):
     """logits x10: near one-hot posteriors; products underflow, eps terms matter."""
     ids, py, logits, mask = _random_case(21, 48, 3, 3000, 4, 90, False, scale=20.0)

@@ -324,6 +324,24 @@ def test_no_cpu_fallback(eodm):
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace("# oracle-free", ""), f
 
 
+def test_tf_drop_in_imports_no_torch_and_shim_compiles():
+    """What the TF drop-in imports (tf_shim/utils/ngram_tools.py -> eodm_b200.tools) must not pull PyTorch into a
+    TensorFlow process, and the custom-op source must compile against the stand-in TF headers."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import eodm_b200.tools, eodm_b200; "
+            "from eodm_b200.tools import load_vocab, ngram2kernel, read_ngram; "
+            "assert 'torch' not in sys.modules, 'torch was imported'; "
+            "import eodm_b200 as E; E.P_Ngram; assert 'torch' in sys.modules" % os.path.join(ROOT, "unsupervised-asr_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    shim = os.path.join(ROOT, "unsupervised-asr_b200", "tf_shim")
+    out = subprocess.run(["make", "-C", shim, "-B", "check"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    src = open(os.path.join(shim, "models", "EODM.py")).read() + open(os.path.join(shim, "utils", "ngram_tools.py")).read()
+    assert "import torch" not in src
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the arm the driver runs beside ours): stdout is exactly one JSON record with the
     contract's keys, on the reference's own CPU-runnable shape; needs no GPU and no CUDA library."""
@@ -340,4 +358,5 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "timit_ref"
+    assert d["config"]["workload"] == "timit_ref" and d["config"]["B_per_gpu"] == 1000
+    assert "all 1000 utterances" in d["cpu_baseline"]["sample"]

@@ -32,6 +32,19 @@
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// Makes `device` current and restores the caller's device on EVERY exit from the scope.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device) {
+    cudaGetDevice(&prev);
+    err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 extern "C" int eodm_version(void) { return EODM_B200_VERSION; }
 
 static int check_batch(const eodm_table* t, const void* px, const void* mask, int B, int T) {
@@ -39,7 +52,9 @@ static int check_batch(const eodm_table* t, const void* px, const void* mask, in
   REQUIRE(t->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
   REQUIRE(B >= 1 && T >= 1, EODM_ESHAPE, "need B >= 1 and T >= 1 (B=%d T=%d)", B, T);
   REQUIRE(T >= t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, t->n);
-  REQUIRE(aligned16(px), EODM_EINVAL, "px must be 16-byte aligned");
+  // rows of V floats are read as float4 only when V is a multiple of 4 (the half-batch offsets of the session keep the
+  // alignment then); other widths take the scalar paths and need no alignment
+  REQUIRE((t->V & 3) != 0 || aligned16(px), EODM_EINVAL, "px must be 16-byte aligned when V is a multiple of 4");
   return EODM_OK;
 }
 
@@ -100,16 +115,29 @@ extern "C" int eodm_counts_partial(const eodm_table* t, const float* px, const u
   return eodm_counts_fwd_launch(t, px, mask, B, T, S, nullptr, Kw, ws, (cudaStream_t)stream);
 }
 
-extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
-                               const float* gS, float* dpx, void* ws, void* stream) {
+static int counts_bwd_any(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
+                          float* dpx, void* ws, void* stream, int accumulate) {
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
   if (use_tensor_bwd(t))
     return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t) + tc_ws_aligned(t),
-                           (cudaStream_t)stream);
-  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream);
+                           (cudaStream_t)stream, accumulate);
+  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate);
 }
+
+extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                               const float* gS, float* dpx, void* ws, void* stream) {
+  return counts_bwd_any(t, px, mask, B, T, gS, dpx, ws, stream, 0);
+}
+
+// dpx += ...: the VJP of one more table over the same posterior sequence (one P_Ngram per order)
+extern "C" int eodm_counts_bwd_acc(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
+                                   const float* gS, float* dpx, void* ws, void* stream) {
+  return counts_bwd_any(t, px, mask, B, T, gS, dpx, ws, stream, 1);
+}
+
+extern "C" int eodm_table_uses_tensor_vjp(const eodm_table* t) { return t && t->device >= 0 && use_tensor_bwd(t) ? 1 : 0; }
 
 extern "C" int eodm_loss_from_counts(const float* S, const float* N, const float* py, int K, float eps, float* loss,
                                      float* gS, void* stream) {
@@ -440,16 +468,11 @@ extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, cons
   REQUIRE(B >= 1 && B <= s->maxB && T >= 1 && T <= s->maxT, EODM_ESHAPE,
           "batch [%d,%d] exceeds the session's [%d,%d]", B, T, s->maxB, s->maxT);
   REQUIRE(T >= s->t->n, EODM_ESHAPE, "T=%d < kernel_size=%d: Conv1D 'valid' has no output", T, s->t->n);
-  int prev = -1;
-  cudaGetDevice(&prev);
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
+  CUDA_TRY(guard.err);
   const size_t rows = (size_t)B * T, el = rows * s->t->V * sizeof(float);
   // copies worth overlapping (>= 2 MiB each way) and two non-empty halves
-  if (B >= 2 && el >= ((size_t)2 << 20)) {
-    int rc = session_loss_pipelined(s, logits_host, mask_host, B, T, comm, loss_host, dlogits_host);
-    if (prev >= 0) cudaSetDevice(prev);
-    return rc;
-  }
+  if (B >= 2 && el >= ((size_t)2 << 20)) return session_loss_pipelined(s, logits_host, mask_host, B, T, comm, loss_host, dlogits_host);
   int rc = EODM_OK;
   cudaError_t e = cudaMemcpyAsync(s->logits, logits_host, el, cudaMemcpyHostToDevice, s->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->mask, mask_host, rows, cudaMemcpyHostToDevice, s->st);
@@ -461,7 +484,6 @@ extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, cons
   if (e == cudaSuccess && rc == EODM_OK)
     e = cudaMemcpyAsync(loss_host, s->loss, sizeof(float), cudaMemcpyDeviceToHost, s->st);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamSynchronize(s->st);
-  if (prev >= 0) cudaSetDevice(prev);
   if (rc != EODM_OK) return rc;
   if (e != cudaSuccess) {
     eodm_set_error("eodm_session_loss: %s", cudaGetErrorString(e));
@@ -502,9 +524,8 @@ extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logit
   REQUIRE(slot == 0 || slot == 1, EODM_EINVAL, "slot %d (two steps can be in flight: 0 or 1)", slot);
   REQUIRE(B >= 1 && B <= s->maxB && T >= s->t->n && T <= s->maxT, EODM_ESHAPE,
           "batch [%d,%d] does not fit the session's [%d,%d] (kernel_size %d)", B, T, s->maxB, s->maxT, s->t->n);
-  int prev = -1;
-  cudaGetDevice(&prev);
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
+  CUDA_TRY(guard.err);
   int rc = session_slots_init(s);
   if (rc != EODM_OK) return rc;
   eodm_session::Slot& sl = s->slot[slot];
@@ -550,7 +571,6 @@ extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logit
                           cudaMemcpyDeviceToHost, s->d2h_st);
   }
   if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(sl.done, s->d2h_st);
-  if (prev >= 0) cudaSetDevice(prev);
   if (rc != EODM_OK) return rc;
   if (e != cudaSuccess) {
     eodm_set_error("eodm_session_submit: %s", cudaGetErrorString(e));
@@ -575,6 +595,123 @@ extern "C" int eodm_session_wait(eodm_session* s, int slot) {
 }
 
 // pinned host memory for callers without a CUDA binding of their own
+// ---------------------------------------------------------------------------
+// several tables over ONE posterior sequence: one softmax, one packed exchange, one softmax VJP
+// (one P_Ngram per order with kernel_size = order -- SURVEY.md 8d config 3; the reference builds its table per run at
+// main_EODM.py:56-61 and applies it at :164)
+// ---------------------------------------------------------------------------
+struct eodm_multi {
+  int n, device, maxB, maxT, V;
+  const eodm_table* t[EODM_MULTI_MAX];
+  int off[EODM_MULTI_MAX];   // table o's [S (K_o floats), N] block inside `counts`
+  int total;                 // sum over tables of K_o + 1
+  float w[EODM_MULTI_MAX];
+  float *px, *dpx, *counts, *gS, *py;   // gS, py: the K_o vectors back to back (offset off[o] - o)
+  unsigned* done;
+  void* ws;
+  EodmMultiLossArgs la;
+};
+
+static void multi_free(eodm_multi* m) {
+  if (!m) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(m->device);
+  cudaFree(m->px); cudaFree(m->dpx); cudaFree(m->counts); cudaFree(m->gS); cudaFree(m->py); cudaFree(m->done); cudaFree(m->ws);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete m;
+}
+
+extern "C" int eodm_multi_create(const eodm_table* const* tables, const float* const* py_host, const float* weights,
+                                 int n_tables, int maxB, int maxT, eodm_multi** out) {
+  REQUIRE(tables && py_host && out, EODM_EINVAL, "null pointer");
+  REQUIRE(n_tables >= 1 && n_tables <= EODM_MULTI_MAX, EODM_ESHAPE, "n_tables=%d (1..%d)", n_tables, EODM_MULTI_MAX);
+  *out = nullptr;
+  int n_max = 1;
+  for (int o = 0; o < n_tables; ++o) {
+    REQUIRE(tables[o] && py_host[o], EODM_EINVAL, "null table or prior");
+    REQUIRE(tables[o]->device >= 0, EODM_EINVAL, "host-only table: there is no CPU implementation of this path");
+    REQUIRE(tables[o]->V == tables[0]->V && tables[o]->device == tables[0]->device, EODM_ESHAPE,
+            "table %d: V=%d on device %d, table 0: V=%d on device %d", o, tables[o]->V, tables[o]->device, tables[0]->V,
+            tables[0]->device);
+    if (tables[o]->n > n_max) n_max = tables[o]->n;
+  }
+  REQUIRE(maxB >= 1 && maxT >= n_max, EODM_ESHAPE, "maxB=%d maxT=%d (largest kernel_size %d)", maxB, maxT, n_max);
+  eodm_multi* m = new (std::nothrow) eodm_multi();
+  REQUIRE(m, EODM_ENOMEM, "out of host memory");
+  memset(m, 0, sizeof(*m));
+  m->n = n_tables;
+  m->device = tables[0]->device;
+  m->maxB = maxB;
+  m->maxT = maxT;
+  m->V = tables[0]->V;
+  size_t ws_bytes = 0;
+  int total = 0;
+  for (int o = 0; o < n_tables; ++o) {
+    m->t[o] = tables[o];
+    m->w[o] = weights ? weights[o] : 1.f;
+    m->off[o] = total;
+    total += tables[o]->K + 1;
+    const size_t b = eodm_workspace_bytes(tables[o], maxB, maxT);
+    if (b > ws_bytes) ws_bytes = b;
+  }
+  m->total = total;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  const size_t el = (size_t)maxB * maxT * m->V * sizeof(float);
+  cudaError_t e = cudaSetDevice(m->device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->px, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->dpx, el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->counts, (size_t)total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->gS, (size_t)total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->py, (size_t)total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->done, 256);
+  if (e == cudaSuccess) e = cudaMemset(m->done, 0, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&m->ws, ws_bytes + 256);
+  for (int o = 0; o < n_tables && e == cudaSuccess; ++o)
+    e = cudaMemcpy(m->py + (m->off[o] - o), py_host[o], (size_t)tables[o]->K * sizeof(float), cudaMemcpyHostToDevice);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    eodm_set_error("multi-order session allocation failed: %s", cudaGetErrorString(e));
+    multi_free(m);
+    return e == cudaErrorMemoryAllocation ? EODM_ENOMEM : EODM_ECUDA;
+  }
+  m->la.n = n_tables;
+  for (int o = 0; o < n_tables; ++o) {
+    m->la.S[o] = m->counts + m->off[o];
+    m->la.N[o] = m->counts + m->off[o] + tables[o]->K;
+    m->la.py[o] = m->py + (m->off[o] - o);
+    m->la.gS[o] = m->gS + (m->off[o] - o);
+    m->la.w[o] = m->w[o];
+    m->la.K[o] = tables[o]->K;
+  }
+  *out = m;
+  return EODM_OK;
+}
+
+extern "C" void eodm_multi_destroy(eodm_multi* m) { multi_free(m); }
+
+extern "C" int eodm_multi_step_device(eodm_multi* m, const float* logits, const uint8_t* mask, int B, int T, void* comm,
+                                      float* loss_out, float* dlogits, void* stream) {
+  REQUIRE(m && logits && mask && loss_out, EODM_EINVAL, "null pointer");
+  REQUIRE(B >= 1 && B <= m->maxB && T <= m->maxT, EODM_ESHAPE, "batch [%d,%d] exceeds the session's [%d,%d]", B, T, m->maxB,
+          m->maxT);
+  for (int o = 0; o < m->n; ++o)
+    REQUIRE(T >= m->t[o]->n, EODM_ESHAPE, "T=%d < kernel_size=%d of table %d: Conv1D 'valid' has no output", T, m->t[o]->n, o);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)B * T;
+  int rc = eodm_softmax_fwd_launch(logits, rows, m->V, m->px, st);
+  for (int o = 0; o < m->n && rc == EODM_OK; ++o)
+    rc = eodm_counts_fwd(m->t[o], m->px, mask, B, T, m->counts + m->off[o], m->counts + m->off[o] + m->t[o]->K, m->ws, st);
+  // ONE collective for every table's [S, N]: the buffer is contiguous
+  if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, m->counts, m->total - 1, m->counts + m->total - 1, st);
+  if (rc == EODM_OK) rc = eodm_loss_multi_launch(m->la, 1e-15f, loss_out, m->done, dlogits != nullptr, st);
+  for (int o = 0; o < m->n && rc == EODM_OK && dlogits; ++o)
+    rc = counts_bwd_any(m->t[o], m->px, mask, B, T, m->gS + (m->off[o] - o), m->dpx, m->ws, st, o > 0 ? 1 : 0);
+  if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(m->px, m->dpx, rows, m->V, dlogits, st);
+  return rc;
+}
+
 extern "C" int eodm_host_alloc(size_t bytes, void** out) {
   REQUIRE(out, EODM_EINVAL, "null pointer");
   CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));

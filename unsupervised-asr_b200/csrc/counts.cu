@@ -508,7 +508,7 @@ template <int DEPTH, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __restrict__ px,
                        const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int n_tiles,
-                       float* __restrict__ dpx) {
+                       float* __restrict__ dpx, int accumulate) {
   constexpr int TS = 32 * R;
   extern __shared__ float smem[];
   const int ld = odd_ld(TS + 2 * (n - 1));
@@ -544,7 +544,9 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
       wm[i] = ok;
       my_valid |= ok != 0.f;
     }
-    if (__syncthreads_or(my_valid)) {
+    const int any_valid = __syncthreads_or(my_valid);
+    if (!any_valid && accumulate) continue;   // nothing to add to this tile's rows
+    if (any_valid) {
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const TrieArg& tr = args.trie[j];
@@ -619,7 +621,10 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
       for (int idx = threadIdx.x; idx < total; idx += kThreads) {
         int r = idx / V, v = idx - r * V;
         long long gr = row0 + r;
-        if (gr < NR) dpx[gr * V + v] = dP[v * ldo + r];
+        if (gr < NR) {
+          if (accumulate) dpx[gr * V + v] += dP[v * ldo + r];   // several tables over one posterior sequence
+          else dpx[gr * V + v] = dP[v * ldo + r];
+        }
       }
     }
   }
@@ -719,14 +724,14 @@ cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mas
 
 template <int DEPTH, int R>
 cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
-                          const Tiling& tl, float* dpx, size_t smem, cudaStream_t st) {
+                          const Tiling& tl, float* dpx, int accumulate, size_t smem, cudaStream_t st) {
   if constexpr (!(R <= 8 || DEPTH <= 5)) {
     return cudaErrorInvalidValue;
   } else {
     auto k = eodm_counts_bwd_kernel<DEPTH, R>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, dpx);
+    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, dpx, accumulate);
     return cudaGetLastError();
   }
 }
@@ -838,7 +843,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 }
 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                           float* dpx, void* ws, cudaStream_t st) {
+                           float* dpx, void* ws, cudaStream_t st, int accumulate) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   Tiling tl;
@@ -883,7 +888,7 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     tr.total_cost = h.total_cost;
     for (int l = 0; l < EODM_MAX_N; ++l) tr.off[l] = (l < n) ? h.pos[l] - j + (n - 1) : 0;
   }
-#define CALL(D, R) launch_bwd_dr<D, R>(a, px, mask, NR, T, V, n, tl, dpx, smem, st)
+#define CALL(D, R) launch_bwd_dr<D, R>(a, px, mask, NR, T, V, n, tl, dpx, accumulate, smem, st)
   EODM_DISPATCH(n, tl.R, CALL)
 #undef CALL
   if (e != cudaSuccess) {

@@ -13,7 +13,7 @@ size_t eodm_counts_workspace_bytes(const eodm_table* t);
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
                            float* W, void* ws, cudaStream_t st);   // W (optional): number of valid window starts
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                           float* dpx, void* ws, cudaStream_t st);
+                           float* dpx, void* ws, cudaStream_t st, int accumulate = 0);   // accumulate: dpx += ...
 
 // tensor.cu -- tcgen05 path for full-order tables
 bool eodm_tc_supported(const eodm_table* t);
@@ -26,11 +26,24 @@ int eodm_tcb_vp(int n, int V, bool full_order);   // padded vocabulary the path 
 bool eodm_tcb_supported(const eodm_table* t);
 size_t eodm_tcb_workspace_bytes(const eodm_table* t);
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
-                    void* ws, cudaStream_t st);
+                    void* ws, cudaStream_t st, int accumulate = 0);
 
 // ops.cu -- loss, softmax, materialising op
 int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
                      cudaStream_t st);
+// several tables at once: block o handles table o; loss_out[o] = w[o] * loss_o, loss_out[n] = their sum; gS_o scaled by w[o]
+#define EODM_MULTI_MAX 8
+struct EodmMultiLossArgs {
+  const float* S[EODM_MULTI_MAX];
+  const float* N[EODM_MULTI_MAX];
+  const float* py[EODM_MULTI_MAX];
+  float* gS[EODM_MULTI_MAX];
+  float w[EODM_MULTI_MAX];
+  int K[EODM_MULTI_MAX];
+  int n;
+};
+int eodm_loss_multi_launch(const EodmMultiLossArgs& a, float eps, float* loss_out, unsigned* done_counter, bool need_grad,
+                           cudaStream_t st);
 int eodm_add_vectors_launch(const float* a, const float* b, int n, float* out, cudaStream_t st);
 int eodm_softmax_fwd_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st);
 bool eodm_softmax_rows4_launch(const float* logits, int64_t rows, int V, float* px, cudaStream_t st);  // aux_ops.cu

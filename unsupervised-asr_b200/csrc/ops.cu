@@ -48,6 +48,47 @@ __global__ void __launch_bounds__(1024) eodm_loss_kernel(const float* __restrict
   }
 }
 
+// The same for several tables in one launch (one P_Ngram per order over ONE posterior sequence): block o handles table o
+// with the summation order of eodm_loss_kernel; the block that finishes last adds the weighted losses in table order.
+__global__ void __launch_bounds__(1024) eodm_loss_multi_kernel(const __grid_constant__ EodmMultiLossArgs a, float eps,
+                                                               float* __restrict__ loss_out, unsigned* __restrict__ done,
+                                                               int need_grad) {
+  __shared__ float red[32];
+  __shared__ unsigned last;
+  const int o = blockIdx.x;
+  const float* S = a.S[o];
+  const float* py = a.py[o];
+  float* gS = need_grad ? a.gS[o] : nullptr;
+  const float n = a.N[o][0], w = a.w[o];
+  float acc = 0.f;
+  for (int z = threadIdx.x; z < a.K[o]; z += blockDim.x) {
+    const float pz = S[z] / n;
+    const float p = py[z];
+    acc += -p * logf(pz + eps);
+    if (gS) gS[z] = w * (-p / (pz + eps) / n);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      loss_out[o] = w * v;
+      __threadfence();
+      last = atomicAdd(done, 1u) == (unsigned)a.n - 1u;
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float total = 0.f;
+    for (int k = 0; k < a.n; ++k) total += ((volatile float*)loss_out)[k];
+    loss_out[a.n] = total;
+    *done = 0;   // ready for the next step (graph replays included)
+  }
+}
+
 // Softmax over rows of V floats.  A row is held in registers by a group of G lanes (G = 1..32, a power of two,
 // 4 floats per lane), so a warp covers 32/G rows with one vectorised read and one vectorised write per element:
 // HBM-bound (8 B per element forward, 12 B backward).  Rows wider than 128 floats take the generic warp-per-row path.
@@ -219,6 +260,17 @@ __global__ void __launch_bounds__(256) eodm_add_vectors_kernel(const float* __re
   if (i < n) out[i] = a[i] + b[i];
 }
 }  // namespace
+
+int eodm_loss_multi_launch(const EodmMultiLossArgs& a, float eps, float* loss_out, unsigned* done_counter, bool need_grad,
+                           cudaStream_t st) {
+  eodm_loss_multi_kernel<<<a.n, 1024, 0, st>>>(a, eps, loss_out, done_counter, need_grad ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_loss_multi_kernel launch failed: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
 
 int eodm_add_vectors_launch(const float* a, const float* b, int n, float* out, cudaStream_t st) {
   eodm_add_vectors_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, n, out);

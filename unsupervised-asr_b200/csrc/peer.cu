@@ -32,6 +32,7 @@ struct PeerView {
   char* base[kMaxPeers];
   int world, rank, K;
   unsigned long long slot_bytes;
+  long long timeout_clk;   // give up waiting for a peer after this many SM clocks; <= 0: wait for ever
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kThreadsP) eodm_peer_loss_kernel(const __grid_
     const long long t0 = clock64();
     // steps are compared as signed differences: the counter may wrap
     while ((int)(ld_acquire_sys(flag) - step) < 0) {
-      if (clock64() - t0 > (20LL << 30)) {   // ~10 s: a peer never arrived; report instead of hanging the GPU
+      if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {   // a peer never arrived: report instead of hanging
         s_bad = 1;
         break;
       }
@@ -88,9 +89,17 @@ __global__ void __launch_bounds__(kThreadsP) eodm_peer_loss_kernel(const __grid_
   }
   __syncthreads();
   if (s_bad) {
+    // fail loudly and deterministically: NaN in every output, so that nothing downstream (the VJP, a gradient
+    // all-reduce) can silently mix garbage with the late peer's good step
+    const float nan = __int_as_float(0x7fc00000);
+    for (int z = threadIdx.x; z < K; z += kThreadsP) {
+      if (gS) gS[z] = nan;
+      if (counts_out) counts_out[z] = nan;
+    }
     if (threadIdx.x == 0) {
       *reinterpret_cast<int*>(mine + 128) = 1;
-      loss[0] = __int_as_float(0x7fc00000);
+      loss[0] = nan;
+      if (counts_out) counts_out[K] = nan;
     }
     return;
   }
@@ -167,6 +176,7 @@ extern "C" int eodm_peer_create(int world, int rank, int K, eodm_peer** out, cha
   p->pv.rank = rank;
   p->pv.K = K;
   p->pv.slot_bytes = (((size_t)K + 1) * sizeof(float) + 255) & ~(size_t)255;
+  p->pv.timeout_clk = 120LL * 2000000000LL;   // ~2 minutes of SM clocks: checkpoints, evals and first-step JITs are shorter
   const size_t bytes = kHdrBytes + 3 * p->pv.slot_bytes;   // two peer-visible slots + a private plane for the sums
   cudaError_t e = cudaGetDevice(&p->device);
   void* mem = nullptr;
@@ -236,6 +246,14 @@ extern "C" int eodm_peer_loss(eodm_peer* p, const float* counts, const float* py
     eodm_set_error("eodm_peer_loss_kernel launch failed: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
   }
+  return EODM_OK;
+}
+
+// How long eodm_peer_loss waits for a late peer before it gives up (every output NaN, eodm_peer_failed() = 1);
+// seconds <= 0: wait for ever.  Default: about two minutes.
+extern "C" int eodm_peer_set_timeout(eodm_peer* p, double seconds) {
+  PEER_REQUIRE(p, EODM_EINVAL, "null pointer");
+  p->pv.timeout_clk = seconds > 0 ? (long long)(seconds * 2.0e9) : 0;
   return EODM_OK;
 }
 

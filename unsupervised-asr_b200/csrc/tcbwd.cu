@@ -72,6 +72,7 @@ struct BArgs {
   long long NR;
   int T, V, n_tiles;
   int px_tma;        // 1: the posterior tile is staged by TMA (V % 4 == 0), 0: by loads
+  int accumulate;    // 1: dpx += (several tables over one posterior sequence), 0: dpx =
   long long* prof;   // debug: per-CTA cycle counters (eodm_debug_tcb_profile), nullptr in production
   int dbg;           // debug (timing experiments only, results are wrong): 1 = no TMA, 2 = no epilogue work
 };
@@ -485,7 +486,7 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         for (int idx = te; idx < kTotal; idx += 256) {
           const int r = idx / VP, v = idx - r * VP;
           const float x = dpt[(r + 2) * C::LDP + v] + dpt[(128 + r + 2) * C::LDP + v];
-          if (v < V && r < rows_left) out0[r * V + v] = x;
+          if (v < V && r < rows_left) out0[r * V + v] = a.accumulate ? out0[r * V + v] + x : x;
         }
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");   // the tiles are free for the next dP_0 rows
@@ -624,7 +625,7 @@ size_t eodm_tcb_workspace_bytes(const eodm_table* t) {
 }
 
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
-                    void* ws, cudaStream_t st) {
+                    void* ws, cudaStream_t st, int accumulate) {
   if (!eodm_tcb_supported(t)) {
     eodm_set_error("tensor-core VJP needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -675,6 +676,7 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   BArgs a;
   a.px = px;
   a.px_tma = px_tma ? 1 : 0;
+  a.accumulate = accumulate;
   a.mask = mask;
   a.dpx = dpx;
   a.NR = NR;

@@ -251,10 +251,13 @@ class _ProbFn(torch.autograd.Function):
 class _EodmLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, mask, py, table, comm):
+        # inside forward() grad mode is off: a converted copy (.float() / .contiguous()) no longer requires grad, so ask
+        # autograd whether the INPUT does
+        need = ctx.needs_input_grad[0]
+        ctx.in_dtype = logits.dtype
         logits = _f32c(logits, "_logits")
         px = softmax_fwd(logits)                                   # models/EODM.py:15
         counts = counts_fwd(table, px, mask)                       # :14,18-20 (numerator and N)
-        need = logits.requires_grad
         if comm is not None and hasattr(comm, "fused_loss"):       # batch-sharded step, exchange fused with the loss
             loss, gS, _ = comm.fused_loss(counts, py, need)
         else:
@@ -271,7 +274,7 @@ class _EodmLossFn(torch.autograd.Function):
         px, gS = ctx.saved_tensors
         # everything below is linear in gS: the upstream gradient scales K floats, not [B, T, V]
         dpx = counts_bwd(ctx.table, px, ctx.mask, gS * gout)
-        return softmax_bwd(px, dpx), None, None, None, None
+        return softmax_bwd(px, dpx).to(ctx.in_dtype), None, None, None, None
 
 
 class PNgram:
@@ -440,3 +443,83 @@ def EODM_loss_dense_bigram(_logits, mask, conv_op, k, py):
     if py.numel() != table.K:
         raise EodmError(_lib.ESHAPE, "len(py)=%d != K=%d" % (py.numel(), table.K))
     return _DenseBigramLossFn.apply(_logits, _mask_u8(mask, _logits.device), py, table, conv_op.comm)
+
+
+def uses_tensor_vjp(table):
+    """True if eodm_counts_bwd serves this table with the tcgen05 kernel (csrc/tcbwd.cu) rather than the trie walk."""
+    return bool(lib.eodm_table_uses_tensor_vjp(table._h))
+
+
+class MultiOrderSession:
+    """Several tables over ONE posterior sequence (eodm_multi_* of include/eodm_b200.h): one P_Ngram per order with
+    kernel_size = order, as SURVEY.md 8d config 3 runs orders 1-5.  One softmax, one packed exchange, one softmax VJP
+    per step instead of one of each per table."""
+
+    def __init__(self, conv_ops, pys, maxB, maxT, weights=None):
+        self.tables = [op.table if isinstance(op, PNgram) else op for op in conv_ops]
+        n = len(self.tables)
+        self._pys = [np.ascontiguousarray(p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else p, dtype=np.float32)
+                     for p in pys]
+        for t, p in zip(self.tables, self._pys):
+            if p.size != t.K:
+                raise EodmError(_lib.ESHAPE, "len(py)=%d != K=%d" % (p.size, t.K))
+        tabs = (C.c_void_p * n)(*[t._h for t in self.tables])
+        pyp = (C.c_void_p * n)(*[p.ctypes.data for p in self._pys])
+        w = None
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.float32)
+            assert w.size == n
+        self._h = C.c_void_p()
+        check(lib.eodm_multi_create(tabs, pyp, w.ctypes.data_as(C.c_void_p) if w is not None else None, n, int(maxB),
+                                    int(maxT), C.byref(self._h)))
+        self.n, self.maxB, self.maxT = n, int(maxB), int(maxT)
+        self.device = self.tables[0].device
+
+    def step_device(self, logits_ptr, mask_ptr, B, T, loss_ptr, dlogits_ptr, stream, comm=None):
+        check(lib.eodm_multi_step_device(self._h, C.c_void_p(logits_ptr), C.c_void_p(mask_ptr), int(B), int(T),
+                                         comm.handle if comm is not None else None, C.c_void_p(loss_ptr),
+                                         C.c_void_p(dlogits_ptr) if dlogits_ptr else None, C.c_void_p(stream)))
+
+    def close(self):
+        if self._h:
+            lib.eodm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _MultiLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, mask_u8, sess, comm):
+        need = ctx.needs_input_grad[0]
+        logits = _f32c(logits, "_logits")
+        B, T, V = logits.shape
+        losses = torch.empty(sess.n + 1, dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits) if need else None
+        sess.step_device(logits.data_ptr(), mask_u8.data_ptr(), B, T, losses.data_ptr(), dl.data_ptr() if need else 0,
+                         torch.cuda.current_stream().cuda_stream, comm=comm)
+        ctx.save_for_backward(dl if need else torch.empty(0, device=logits.device))
+        ctx.mark_non_differentiable(losses)
+        return losses[sess.n].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None
+
+
+def EODM_loss_multi(_logits, mask, sess, comm=None):
+    """Sum over tables of EODM_loss(_logits, mask, conv_op_o, K_o, py_o) (models/EODM.py:5-25 applied once per order) as
+    ONE fused step of a MultiOrderSession.  Returns (total, per_table) -- per_table f32[n + 1] holds the weighted losses
+    and, last, their sum; only `total` carries the gradient."""
+    logits = _f32c(_logits, "_logits")
+    if logits.dim() != 3:
+        raise EodmError(_lib.ESHAPE, "_logits must be [B, T, V], got %r" % (tuple(logits.shape),))
+    if logits.shape[0] > sess.maxB or logits.shape[1] > sess.maxT:
+        raise EodmError(_lib.ESHAPE, "batch %r exceeds the session's [%d, %d]" % (tuple(logits.shape[:2]), sess.maxB, sess.maxT))
+    return _MultiLossFn.apply(_logits if _logits.dtype == torch.float32 and _logits.is_contiguous() else logits,
+                              _mask_u8(mask, logits.device), sess, comm)

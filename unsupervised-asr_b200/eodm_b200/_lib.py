@@ -54,11 +54,17 @@ SIGNATURES = {
     "eodm_peer_destroy": (None, [_p]),
     "eodm_peer_loss": (_i, [_p, _p, _p, C.c_float, _p, _p, _p, _p]),
     "eodm_peer_failed": (_i, [_p]),
+    "eodm_peer_set_timeout": (_i, [_p, C.c_double]),
     "eodm_session_set_peer": (_i, [_p, _p]),
     "eodm_session_submit": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p]),
     "eodm_session_wait": (_i, [_p, _i]),
     "eodm_counts_partial": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_counts_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "eodm_counts_bwd_acc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "eodm_table_uses_tensor_vjp": (_i, [_p]),
+    "eodm_multi_create": (_i, [_p, _p, _p, _i, _i, _i, _pp]),
+    "eodm_multi_destroy": (None, [_p]),
+    "eodm_multi_step_device": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_loss_from_counts": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _p]),
     "eodm_softmax_fwd": (_i, [_p, C.c_int64, _i, _p, _p]),
     "eodm_softmax_bwd": (_i, [_p, _p, C.c_int64, _i, _p, _p]),
@@ -93,6 +99,8 @@ _DEBUG_SIGNATURES = {
     "eodm_table_debug_trie": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "eodm_debug_set_tiling": (None, [_i, _i]),
     "eodm_debug_set_path": (None, [_i]),
+    "eodm_debug_tcb_profile": (None, [_p]),
+    "eodm_debug_tcb_switches": (None, [_i]),
 }
 
 for _name, (_res, _args) in list(SIGNATURES.items()) + list(_DEBUG_SIGNATURES.items()):

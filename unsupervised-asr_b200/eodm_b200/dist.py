@@ -27,7 +27,8 @@ def shard_bounds(B, world, rank):
 
 def shard_bounds_by_length(lengths, world):
     """Contiguous slices balanced by sum of lengths (ragged batches).  Returns
-    world+1 boundaries; deterministic greedy cut at the ideal prefix sums."""
+    world+1 boundaries; deterministic greedy cut at the ideal prefix sums.  With at
+    least `world` utterances every shard holds at least one."""
     lengths = np.asarray(lengths, dtype=np.int64)
     csum = np.concatenate([[0], np.cumsum(lengths)])
     total = csum[-1]
@@ -37,7 +38,10 @@ def shard_bounds_by_length(lengths, world):
         i = int(np.searchsorted(csum, target, side="left"))
         if i > 0 and abs(csum[i - 1] - target) <= abs(csum[min(i, len(csum) - 1)] - target):
             i -= 1
-        bounds.append(max(bounds[-1], min(i, len(lengths))))
+        i = max(bounds[-1], min(i, len(lengths)))
+        if len(lengths) >= world:      # no empty shard: a rank without utterances would fail before the collective
+            i = min(max(i, bounds[-1] + 1), len(lengths) - (world - r))
+        bounds.append(i)
     bounds.append(len(lengths))
     return bounds
 
@@ -133,7 +137,18 @@ class PeerGroup:
         """counts: this rank's packed CUDA f32[K+1].  -> (loss f32[1], gS f32[K] or None, global counts or None)."""
         import torch
 
+        from ._lib import EodmError, ESHAPE, EINVAL
         K = self.K
+        # the kernel trusts K: a group bootstrapped for another table would read past these buffers
+        if not (counts.is_cuda and counts.dtype == torch.float32 and counts.is_contiguous() and counts.numel() == K + 1):
+            raise EodmError(ESHAPE, "counts must be a contiguous CUDA f32[K + 1 = %d], got %s %r" %
+                            (K + 1, counts.dtype, tuple(counts.shape)))
+        if not isinstance(py, torch.Tensor):
+            py = torch.as_tensor(py, dtype=torch.float32, device=counts.device)
+        if not (py.is_cuda and py.dtype == torch.float32 and py.is_contiguous() and py.numel() == K):
+            raise EodmError(ESHAPE, "py must be a contiguous CUDA f32[K = %d] (the group was created for K = %d)" % (K, K))
+        if py.device != counts.device:
+            raise EodmError(EINVAL, "py is on %s, counts on %s" % (py.device, counts.device))
         loss = torch.empty(1, dtype=torch.float32, device=counts.device)
         gS = torch.empty(K, dtype=torch.float32, device=counts.device) if need_grad else None
         out = torch.empty(K + 1, dtype=torch.float32, device=counts.device) if want_counts else None
@@ -144,7 +159,12 @@ class PeerGroup:
         return loss, gS, out
 
     def failed(self):
+        """True if a step gave up waiting for a peer (its loss, dloss/dS and counts are NaN).  Synchronises the device."""
         return bool(lib.eodm_peer_failed(self.handle))
+
+    def set_timeout(self, seconds):
+        """How long a step waits for a late peer (seconds <= 0: for ever; default about two minutes)."""
+        check(lib.eodm_peer_set_timeout(self.handle, float(seconds)))
 
     def close(self):
         if self.handle:
