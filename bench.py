@@ -330,13 +330,14 @@ def main():
     dom_is_bwd = t_b >= t_f
     ach = (fl_b / t_b if dom_is_bwd else fl_f / t_f) / 1e12
     bwd_kernel = "eodm_tc_bwd_kernel" if E.uses_tensor_vjp(table) else "eodm_counts_bwd_kernel"
+    fwd_kernel = "eodm_tc_fwd3_kernel" if E.uses_tensor_fwd(table) else "eodm_counts_fwd_kernel"
     roofline = {
-        "kernel": bwd_kernel if dom_is_bwd else "eodm_counts_fwd_kernel",
+        "kernel": bwd_kernel if dom_is_bwd else fwd_kernel,
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
         "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s); CUDA-core FMA peak, not a tensor or HBM figure"
                        % ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "fallback 1965 MHz"),
         "traffic": None,
-        "fwd": {"kernel": "eodm_counts_fwd_kernel", "ms": t_f * 1e3, "flops": fl_f, "tflops": fl_f / t_f / 1e12,
+        "fwd": {"kernel": fwd_kernel, "ms": t_f * 1e3, "flops": fl_f, "tflops": fl_f / t_f / 1e12,
                 "frac": fl_f / t_f / 1e12 / fp32_peak},
         "bwd": {"kernel": bwd_kernel, "ms": t_b * 1e3, "flops": fl_b, "tflops": fl_b / t_b / 1e12,
                 "frac": fl_b / t_b / 1e12 / fp32_peak},
@@ -500,8 +501,10 @@ def main():
             "notes": {"l2": "flushed between timed steps (256 MiB write)",
                       "exchange": None if world == 1 else
                       ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
-                      "path": ("forward: cuda-core trie walk (shared-memory operand tile); VJP: tcgen05 cta_group::2 3xTF32, "
-                               "windows on the M axis, TMA-staged posterior tile" if E.uses_tensor_vjp(table) else
+                      "path": ("forward: %s; VJP: tcgen05 cta_group::2 3xTF32, windows on the M axis, TMA-staged posterior tile"
+                               % ("tcgen05 3xTF32, pairs on the M axis, operand formed in registers and written to TMEM"
+                                  if E.uses_tensor_fwd(table) else "cuda-core trie walk (shared-memory operand tile)")
+                               if E.uses_tensor_vjp(table) else
                                "cuda-core trie walk (shared-memory operand tile, flat tails, node stream two entries ahead)")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss_d.item()),

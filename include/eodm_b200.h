@@ -102,6 +102,7 @@ int eodm_counts_bwd_acc(const eodm_table* t, const float* px, const uint8_t* mas
 /* 1 if eodm_counts_bwd serves this table on the tensor cores (tcgen05; trigram-only tables over V <= 48 that are dense
  * enough), 0 if on the CUDA-core trie walk.  Informational. */
 int eodm_table_uses_tensor_vjp(const eodm_table* t);
+int eodm_table_uses_tensor_fwd(const eodm_table* t);   /* the same for eodm_counts_fwd */
 
 /* loss = -sum_z py[z]*log(S[z]/N + eps);  gS[z] = dloss/dS[z]   (models/EODM.py:20-23)
  * loss f32[1], gS f32[K] (gS may be NULL). */

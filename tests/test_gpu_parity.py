@@ -160,6 +160,50 @@ def test_tensor_core_counts_vs_oracle(eodm, seed, V, n, K, B, T):
 
 
 @pytest.mark.parametrize("seed,V,K,B,T,len_lo,dup", [
+    (1, 48, 10000, 6, 100, None, False),     # BASELINE configs[1] table
+    (2, 48, 3000, 40, 300, 3, True),         # ragged, duplicates, several tiles per slice
+    (3, 40, 5000, 7, 131, 1, False),         # V padded 40 -> 48; lengths down to 1 (< kernel size)
+    (4, 30, 2000, 5, 64, 5, True),
+    (7, 12, 500, 9, 3, None, False),         # T == kernel size: one window per utterance
+    (8, 47, 9000, 1, 126, None, False),      # V % 4 != 0 (scalar staging)
+    (9, 48, 10000, 148, 400, 200, False),    # 59 200 rows: 29 tiles of 128 windows per slice
+    (10, 48, 10000, 3, 5, None, False),      # fewer windows than one stage
+])
+def test_tensor_core_forward_v2_vs_oracle(eodm, seed, V, K, B, T, len_lo, dup):
+    """The tcgen05 forward of a trigram-only table (csrc/tcfwd.cu: pairs on the M axis, the generated operand written
+    straight to TMEM, [hi; lo] of the third position stacked along N), pinned through the debug hook, against the fp64
+    oracle; bit-reproducible; and agreeing with the CUDA-core walk."""
+    from eodm_b200._lib import lib
+    from oracle import fast as F
+    ids, py = eodm.synth.table(V, 3, K, seed=seed, min_id=0 if seed % 2 else 1)
+    if dup:
+        ids[K // 2] = ids[0]
+        ids[K - 1] = ids[0]
+    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=len_lo)
+    if B > 2:
+        mask[1, :] = False
+    dev = _dev()
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
+    m = torch.tensor(mask, device=dev)
+    S_ref, N_ref = F.counts_fwd(px.cpu().numpy().astype(np.float64), mask, ids, 3)
+    try:
+        lib.eodm_debug_set_path(2)
+        c1 = eodm.counts_fwd(table, px, m)
+        c2 = eodm.counts_fwd(table, px, m)
+        lib.eodm_debug_set_path(1)
+        walk = eodm.counts_fwd(table, px, m)
+    finally:
+        lib.eodm_debug_set_path(0)
+    assert torch.equal(c1, c2)
+    got = c1.cpu().numpy()
+    assert got[K] == N_ref
+    big = S_ref > 1e-30
+    assert (np.abs(got[:K][big] - S_ref[big]) / S_ref[big]).max() <= TOL, (np.abs(got[:K][big] - S_ref[big]) / S_ref[big]).max()
+    assert (np.abs(walk.cpu().numpy()[:K][big] - S_ref[big]) / S_ref[big]).max() <= TOL
+
+
+@pytest.mark.parametrize("seed,V,K,B,T,len_lo,dup", [
     (1, 48, 10000, 6, 100, None, False),     # BASELINE configs[1] table; 600 rows = 4.8 tiles of 126
     (2, 48, 3000, 40, 300, 3, True),         # ragged, duplicates, 96 tiles: several tile pairs per CTA pair
     (3, 40, 5000, 7, 131, 1, False),         # V padded 40 -> 48; lengths down to 1 (< kernel size)

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
 }
 
 // ---------------------------------------------------------------- (1a) cta_group::1 timing
-__global__ void __launch_bounds__(128, 1) k_time1(int M, int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128, 1) k_time1(int M, int N, int iters, long long* out, int a_tmem = 0) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
@@ -51,10 +51,18 @@ __global__ void __launch_bounds__(128, 1) k_time1(int M, int N, int iters, long 
     const uint64_t bd = desc_k(smem_u32(B), (uint32_t)N * 16u, 128u);
     const uint64_t ad = desc_k(smem_u32(A), (uint32_t)M * 16u, 128u);
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tmem + (uint32_t)((i & 1) * 256);
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                   ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+    if (a_tmem) {
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t d = tmem + (uint32_t)((i & 1) * 128);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                     ::"r"(d), "r"(tmem + 480u + (uint32_t)((i & 1) * 8)), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+      }
+    } else {
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t d = tmem + (uint32_t)((i & 1) * 256);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     mbar_wait(&bar, 0);
@@ -210,6 +218,10 @@ int main() {
       for (int rep = 0; rep < 2; ++rep) { k_time1<<<148, 128, sm>>>(M, N, iters, out); if (!ok("time1")) return 1; }
       printf("cta_group::1 M=%3d N=%3d: %.1f clk/MMA\n", M, N, (double)out[0] / iters);
     }
+  for (int N : {16, 32, 48, 64, 96, 128}) {
+    for (int rep = 0; rep < 2; ++rep) { k_time1<<<148, 128, sm>>>(128, N, iters, out, 1); if (!ok("time1t")) return 1; }
+    printf("cta_group::1 M=128 N=%3d, A from TMEM: %.1f clk/MMA\n", N, (double)out[0] / iters);
+  }
   for (int M : {128, 256})
     for (int N : {64, 128, 256}) {
       for (int rep = 0; rep < 2; ++rep) { k_time2<<<148, 128, sm>>>(M, N, iters, out); if (!ok("time2")) return 1; }

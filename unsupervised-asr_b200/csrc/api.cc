@@ -66,14 +66,21 @@ static int check_batch(const eodm_table* t, const void* px, const void* mask, in
 static int g_path = 0;
 extern "C" void eodm_debug_set_path(int path) { g_path = path; }
 
-static bool use_tensor_fwd(const eodm_table* t) {
-  if (g_path == 1) return false;
-  if (g_path == 2) return true;
-  return false;  // until the tensor path is the faster one everywhere it applies
+// forward: 0 = trie walk, 2 = tensor.cu (any full-order table), 3 = tcfwd.cu (trigram-only tables over V <= 48)
+static int fwd_path(const eodm_table* t) {
+  if (g_path == 1) return 0;
+  if (g_path == 4) return eodm_tc_supported(t) ? 2 : 0;
+  if (g_path == 2) return eodm_tcf_supported(t) ? 3 : (eodm_tc_supported(t) ? 2 : 0);
+  if (!eodm_tcf_supported(t)) return 0;
+  // measured at timit_c2 (profiles/r02_tcfwd.md): the tensor-core forward costs ~650 SM-clocks per row whatever the table
+  // holds (it is bound by forming the 2304 x W operand, not by the MMAs); the walk costs ~0.057 per trie node and row.
+  const double tc_clk_per_row = 650.0, walk_clk_per_row = 0.0567 * (double)t->trie[0].n_nodes;
+  return tc_clk_per_row < walk_clk_per_row ? 3 : 0;
 }
 
 static size_t counts_ws_aligned(const eodm_table* t) { return (eodm_counts_workspace_bytes(t) + 255) & ~(size_t)255; }
 static size_t tc_ws_aligned(const eodm_table* t) { return (eodm_tc_workspace_bytes(t) + 255) & ~(size_t)255; }
+static size_t tcb_ws_aligned(const eodm_table* t) { return (eodm_tcb_workspace_bytes(t) + 255) & ~(size_t)255; }
 
 // The tensor-core VJP (tcbwd.cu) costs 2 * ceil(VP^2/256) * (VP/8) * 3 MMAs of 128 clk per 126 rows whatever the table
 // holds; the trie walk costs about one shared-memory wavefront per (trie node, 32 rows) in each of its three tries.
@@ -92,7 +99,7 @@ extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
   (void)B;
   (void)T;
   if (!t || t->device < 0) return 0;
-  return counts_ws_aligned(t) + tc_ws_aligned(t) + eodm_tcb_workspace_bytes(t);
+  return counts_ws_aligned(t) + tc_ws_aligned(t) + tcb_ws_aligned(t) + eodm_tcf_workspace_bytes(t);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -100,7 +107,11 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
-  if (use_tensor_fwd(t))
+  const int path = fwd_path(t);
+  if (path == 3)
+    return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tc_ws_aligned(t) + tcb_ws_aligned(t),
+                           (cudaStream_t)stream);
+  if (path == 2)
     return eodm_tc_fwd_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t), (cudaStream_t)stream);
   return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream);
 }
@@ -138,6 +149,7 @@ extern "C" int eodm_counts_bwd_acc(const eodm_table* t, const float* px, const u
 }
 
 extern "C" int eodm_table_uses_tensor_vjp(const eodm_table* t) { return t && t->device >= 0 && use_tensor_bwd(t) ? 1 : 0; }
+extern "C" int eodm_table_uses_tensor_fwd(const eodm_table* t) { return t && t->device >= 0 && fwd_path(t) != 0 ? 1 : 0; }
 
 extern "C" int eodm_loss_from_counts(const float* S, const float* N, const float* py, int K, float eps, float* loss,
                                      float* gS, void* stream) {

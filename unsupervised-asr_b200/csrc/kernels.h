@@ -21,6 +21,12 @@ size_t eodm_tc_workspace_bytes(const eodm_table* t);
 int eodm_tc_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
                        void* ws, cudaStream_t st);
 
+// tcfwd.cu -- tcgen05 forward for trigram-only tables over V <= 48 (second generation of tensor.cu)
+bool eodm_tcf_supported(const eodm_table* t);
+size_t eodm_tcf_workspace_bytes(const eodm_table* t);
+int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N, void* ws,
+                    cudaStream_t st);
+
 // tcbwd.cu -- tcgen05 VJP for trigram-only tables over V <= 64
 int eodm_tcb_vp(int n, int V, bool full_order);   // padded vocabulary the path would use, 0 = not applicable
 bool eodm_tcb_supported(const eodm_table* t);

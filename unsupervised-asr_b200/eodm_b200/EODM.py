@@ -450,6 +450,11 @@ def uses_tensor_vjp(table):
     return bool(lib.eodm_table_uses_tensor_vjp(table._h))
 
 
+def uses_tensor_fwd(table):
+    """True if eodm_counts_fwd serves this table with a tcgen05 kernel (csrc/tcfwd.cu) rather than the trie walk."""
+    return bool(lib.eodm_table_uses_tensor_fwd(table._h))
+
+
 class MultiOrderSession:
     """Several tables over ONE posterior sequence (eodm_multi_* of include/eodm_b200.h): one P_Ngram per order with
     kernel_size = order, as SURVEY.md 8d config 3 runs orders 1-5.  One softmax, one packed exchange, one softmax VJP

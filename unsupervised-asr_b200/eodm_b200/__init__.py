@@ -20,7 +20,7 @@ from . import synth  # noqa: F401
 _TORCH_SIDE = {name: "EODM" for name in (
     "P_Ngram", "EODM_loss", "PNgram", "NgramTable", "softmax_fwd", "softmax_bwd", "counts_fwd", "counts_bwd",
     "loss_from_counts", "bigram_dense_fwd", "bigram_dense_bwd", "EODM_loss_dense_bigram", "EODM", "counts_partial",
-    "MultiOrderSession", "EODM_loss_multi", "uses_tensor_vjp")}
+    "MultiOrderSession", "EODM_loss_multi", "uses_tensor_vjp", "uses_tensor_fwd")}
 
 
 def _load_torch_side():

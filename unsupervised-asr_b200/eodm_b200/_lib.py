@@ -62,6 +62,7 @@ SIGNATURES = {
     "eodm_counts_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_counts_bwd_acc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eodm_table_uses_tensor_vjp": (_i, [_p]),
+    "eodm_table_uses_tensor_fwd": (_i, [_p]),
     "eodm_multi_create": (_i, [_p, _p, _p, _i, _i, _i, _pp]),
     "eodm_multi_destroy": (None, [_p]),
     "eodm_multi_step_device": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
