@@ -196,6 +196,16 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
     // warp's stores are consecutive 16-byte units of one phone row (Pe) or fall 1552 bytes apart (B): no bank conflicts.
     const int t128 = tid - 256, sw = warp - 8;
     const bool vec = (V & 3) == 0;
+    // The phone chunk of an item rotates with the lane: q = (sw + 4 it + L) mod 12.  With the same chunk in every lane, the
+    // reads of the raw tile (rows 4 L + rr, 48 floats apart: 48 L mod 8 = 0 sixteen-byte units) put all eight lanes of a
+    // quarter warp on the same four banks -- 16.6 M of the kernel's 32.8 M shared-memory load wavefronts were those
+    // conflicts (profiles/r02_tcfwd.md).  Rotated, the reads fall on units (4 rr + q0 + L) mod 8 and the transposed stores
+    // on (4 q0 + kk + 5 L) mod 8: eight different units for eight consecutive lanes, both ways.
+    const int qrot = lane % (kVP / 4);
+    auto qof = [&](int it) {
+      const int q = sw + 4 * it + qrot;
+      return q >= kVP / 4 ? q - kVP / 4 : q;
+    };
     __shared__ __align__(16) float ok_s[2][kTile];
     float* raw = tile0 + 2 * kTileFloats;
     auto issue_raw = [&](int k) {
@@ -241,14 +251,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
 #pragma unroll
           for (int rr = 0; rr < 6; ++rr) {
             const int r = 4 * lane + rr;
-            ld[it][rr] = (r < 130 && inr[rr]) ? *reinterpret_cast<const float4*>(raw + r * V + 4 * (sw + 4 * it))
+            ld[it][rr] = (r < 130 && inr[rr]) ? *reinterpret_cast<const float4*>(raw + r * V + 4 * qof(it))
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * (sw + 4 * it) >= V) ld[it][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * qof(it) >= V) ld[it][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
       } else {
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
-          const int q = sw + 4 * it;
+          const int q = qof(it);
 #pragma unroll
           for (int rr = 0; rr < 6; ++rr) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       if (k >= 2) mbar_wait(&bars.pt_free[buf], (uint32_t)(((k >> 1) - 1) & 1));   // producers and MMAs are done with tile k-2
 #pragma unroll
       for (int it = 0; it < 3; ++it) {
-        const int q = sw + 4 * it;
+        const int q = qof(it);
         float rows[6][4];
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.a_full[g][s]);
+        if (elect_one_f()) mbar_arrive(&bars.a_full[g][s]);
         // the previous round's accumulators, once this round's first stage is on its way
         if (i > 0 && (i % kStPerTile) == 0) drain(i / kStPerTile - 1);
       }
