@@ -142,7 +142,9 @@ int eodm_prob_bwd(const eodm_table* t, const float* px, const float* dp, int B, 
 
 /* ---- dense bigram contraction for large vocabularies (tcgen05, 3xTF32) ---- */
 /* C[u][v] = sum_{b, t <= T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps),  C f32[V][V].
- * V must be a multiple of 128.  ws: eodm_bigram_workspace_bytes. */
+ * Any V >= 2: a V that is not a multiple of 128 (the 3 674 characters of configs/hkust/hkust_char_CTC.yaml:17) runs on
+ * planes padded to the next multiple inside the workspace, at the price of one extra pass over C / G / dpx; px then needs
+ * no alignment.  ws: eodm_bigram_workspace_bytes. */
 size_t eodm_bigram_workspace_bytes(int B, int T, int V);
 int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B, int T, int V, float* C, float* N,
                           void* ws, void* stream);

@@ -433,10 +433,12 @@ def test_full_size_properties(eodm):
 
 
 @pytest.mark.parametrize("B,T,V,ragged", [(2, 9, 128, False), (3, 40, 256, True), (4, 33, 384, True), (6, 50, 1024, True),
-                                            (20, 64, 1024, True)])
+                                            (20, 64, 1024, True), (3, 21, 100, True), (2, 17, 131, True), (3, 12, 1001, True),
+                                            (2, 10, 3674, True)])
 def test_dense_bigram_tcgen05_vs_oracle(eodm, B, T, V, ragged):
     """eodm_bigram_dense_fwd/bwd (TMA-fed tcgen05, 3xTF32, TMEM accumulators drained every 16 K-steps) vs the fp64
-    oracle."""
+    oracle; vocabularies that are not a multiple of 128 (odd row pitch, the 3 674 characters of
+    configs/hkust/hkust_char_CTC.yaml:17) go through the planes padded inside the workspace."""
     dev = _dev()
     logits, mask = O.synth_batch(B, T, V, seed=B, len_lo=2 if ragged else None, scale=3.0)
     px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
@@ -456,8 +458,8 @@ def test_dense_bigram_tcgen05_vs_oracle(eodm, B, T, V, ragged):
     # the VJP on the forward's workspace (operand planes reused) gives the bits of the stand-alone VJP
     assert torch.equal(eodm.bigram_dense_bwd(px, m, torch.tensor(G, device=dev), ws=ws), torch.tensor(d, device=dev))
     with pytest.raises(eodm.EodmError) as e:
-        eodm.bigram_dense_fwd(px[:, :, :100].contiguous(), m)       # V not a multiple of 128
-    assert e.value.status == -5
+        eodm.bigram_dense_fwd(px[:, :1].contiguous(), m[:, :1].contiguous())       # T < kernel_size
+    assert e.value.status == -2
 
 
 def test_dense_bigram_agrees_with_table_path(eodm):
@@ -580,6 +582,23 @@ def test_dense_bigram_loss_equals_table_loss(eodm):
     for loss, grad in out:
         assert abs(loss - r["loss"]) <= TOL * abs(r["loss"])
         assert rel_max(grad, r["dlogits"]) <= TOL and rel_l2(grad, r["dlogits"]) <= TOL
+
+
+def test_dense_bigram_loss_at_hkust_vocabulary(eodm):
+    """EODM_loss for a bigram table over the 3 674 characters of configs/hkust/hkust_char_CTC.yaml:17 -- beyond the walk's
+    vocabulary limit and not a multiple of 128: the dense path pads inside its workspace.  Checked against the oracle."""
+    dev = _dev()
+    V, B, T, K = 3674, 3, 14, 6000
+    ids, py = eodm.synth.table(V, 2, K, seed=3, min_id=0)
+    logits, mask = O.synth_batch(B, T, V, seed=3, len_lo=4, scale=3.0)
+    conv_op = eodm.PNgram(eodm.NgramTable.from_ids(ids, V, device=0))
+    lg = torch.tensor(logits, device=dev, requires_grad=True)
+    loss = eodm.EODM_loss_dense_bigram(lg, torch.tensor(mask, device=dev), conv_op, K, py)
+    loss.backward()
+    r = O.eodm_loss_direct(logits, mask, ids, 2, py)
+    assert abs(float(loss) - r["loss"]) <= TOL * abs(r["loss"])
+    g = lg.grad.cpu().numpy()
+    assert rel_max(g, r["dlogits"]) <= TOL and rel_l2(g, r["dlogits"]) <= TOL
 
 
 @pytest.mark.parametrize("V,n,K,B,T", [(64, 3, 60000, 3, 70),      # K too large for shared-memory accumulators

@@ -109,6 +109,51 @@ __global__ void __launch_bounds__(256) eodm_bigram_split_lo_kernel(const float4*
   }
 }
 
+// ---- vocabularies that are not a multiple of 128 (e.g. the 3 674 characters of configs/hkust/hkust_char_CTC.yaml:17):
+//      the operand planes, C, G and the gradient live in the workspace with a row pitch of Vp = V rounded up to 128; the
+//      columns V..Vp-1 are zero, so the GEMMs see an ordinary multiple-of-128 problem whose extra outputs are never read.
+__global__ void __launch_bounds__(256) eodm_bigram_split_px_pad_kernel(const float* __restrict__ px, const float* __restrict__ wv,
+                                                                       long long NR, int V, int Vp, float eps,
+                                                                       float4* __restrict__ E, float4* __restrict__ Elo,
+                                                                       float4* __restrict__ Xa, float4* __restrict__ Xalo) {
+  const int Vp4 = Vp / 4;
+  const long long n4 = NR * Vp4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Vp4;
+    const int c = (int)(i - r * Vp4) * 4;
+    const float w = __ldg(wv + r);
+    float e[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      e[k] = (c + k < V) ? __ldg(px + r * V + c + k) + eps : 0.f;
+      const float rem = e[k] - __uint_as_float(__float_as_uint(e[k]) & 0xffffe000u);
+      l[k] = __uint_as_float((__float_as_uint(rem) + 0x1000u) & 0xffffe000u);
+    }
+    E[i] = make_float4(e[0], e[1], e[2], e[3]);
+    Elo[i] = make_float4(l[0], l[1], l[2], l[3]);
+    Xa[i] = make_float4(w * e[0], w * e[1], w * e[2], w * e[3]);
+    Xalo[i] = make_float4(w * l[0], w * l[1], w * l[2], w * l[3]);
+  }
+}
+// dst[r][c] (pitch V) = src[r][c] (pitch Vp), r < rows, c < V
+__global__ void __launch_bounds__(256) eodm_bigram_unpad_kernel(const float* __restrict__ src, long long rows, int V, int Vp,
+                                                                float* __restrict__ dst) {
+  const long long n = rows * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / V;
+    dst[i] = __ldg(src + r * Vp + (i - r * V));
+  }
+}
+// dst[r][c] (pitch Vp, Vp rows) = src[r][c] (pitch V) for r, c < V, else 0
+__global__ void __launch_bounds__(256) eodm_bigram_pad_kernel(const float* __restrict__ src, int V, int Vp, float* __restrict__ dst) {
+  const long long n = (long long)Vp * Vp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Vp;
+    const int c = (int)(i - r * Vp);
+    dst[i] = (r < V && c < V) ? __ldg(src + r * V + c) : 0.f;
+  }
+}
+
 int sm_count_of_current_device() {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -118,11 +163,15 @@ int sm_count_of_current_device() {
 
 }  // namespace
 
-// workspace: [wv: B*T f32][cnt: i32][E, E_lo, Xa, Xa_lo: B*T*V f32 each][G_lo: V*V f32], every array 1 KiB aligned
+// workspace: [wv: B*T f32][cnt: i32][E, E_lo, Xa, Xa_lo: B*T*Vp f32 each][G_lo: Vp*Vp f32], every array 1 KiB aligned;
+// Vp = V rounded up to 128, and when Vp != V two more arrays: [CG: Vp*Vp f32 (C of the forward, then G of the VJP)]
+// [dpx_p: B*T*Vp f32]
+static inline int vpad(int V) { return (V + 127) / 128 * 128; }
 extern "C" size_t eodm_bigram_workspace_bytes(int B, int T, int V) {
-  const size_t nr = (size_t)B * T, plane = (nr * V * sizeof(float) + 1023) & ~(size_t)1023;
-  return ((nr * sizeof(float) + 512 + 1023) & ~(size_t)1023) + 4 * plane + (((size_t)V * V * sizeof(float) + 1023) & ~(size_t)1023) +
-         2048;
+  const int Vp = vpad(V);
+  const size_t nr = (size_t)B * T, plane = (nr * Vp * sizeof(float) + 1023) & ~(size_t)1023;
+  const size_t sq = ((size_t)Vp * Vp * sizeof(float) + 1023) & ~(size_t)1023;
+  return ((nr * sizeof(float) + 512 + 1023) & ~(size_t)1023) + 4 * plane + sq + (Vp != V ? sq + plane : 0) + 2048;
 }
 
 namespace {
@@ -130,19 +179,24 @@ struct BigramWs {
   float* wv;
   int* cnt;
   float *E, *Elo, *Xa, *Xalo, *Glo;
+  float *CG, *dpxp;   // padded mode only
 };
 BigramWs carve(void* ws, long long NR, int V) {
+  const int Vp = vpad(V);
   BigramWs w;
   uintptr_t p = ((uintptr_t)ws + 1023) & ~(uintptr_t)1023;
   w.wv = (float*)p;
   w.cnt = (int*)(w.wv + NR);
   p += ((size_t)NR * sizeof(float) + 512 + 1023) & ~(size_t)1023;
-  const size_t plane = ((size_t)NR * V * sizeof(float) + 1023) & ~(size_t)1023;
+  const size_t plane = ((size_t)NR * Vp * sizeof(float) + 1023) & ~(size_t)1023;
+  const size_t sq = ((size_t)Vp * Vp * sizeof(float) + 1023) & ~(size_t)1023;
   w.E = (float*)p;
   w.Elo = (float*)(p + plane);
   w.Xa = (float*)(p + 2 * plane);
   w.Xalo = (float*)(p + 3 * plane);
   w.Glo = (float*)(p + 4 * plane);
+  w.CG = (float*)(p + 4 * plane + sq);
+  w.dpxp = (float*)(p + 4 * plane + 2 * sq);
   return w;
 }
 int fail_launch(const char* what, cudaError_t e) {
@@ -173,11 +227,11 @@ static int bigram_check(const void* px, const void* mask, int B, int T, int V, c
     eodm_set_error("T=%d < kernel_size=2: Conv1D 'valid' has no output", T);
     return EODM_ESHAPE;
   }
-  if (V < 128 || (V % 128) != 0) {
-    eodm_set_error("dense bigram path needs V to be a multiple of 128 (V=%d); smaller vocabularies use the table path", V);
-    return EODM_EUNSUPPORTED;
+  if (V < 2) {
+    eodm_set_error("dense bigram path needs V >= 2 (V=%d)", V);
+    return EODM_ESHAPE;
   }
-  if (((uintptr_t)px & 15) != 0) {
+  if ((V % 128) == 0 && ((uintptr_t)px & 15) != 0) {   // other V go through the padded planes, read with scalar loads
     eodm_set_error("px must be 16-byte aligned");
     return EODM_EINVAL;
   }
@@ -191,15 +245,20 @@ static int bigram_prep(const float* px, const uint8_t* mask, long long NR, int T
   if (e != cudaSuccess) return fail_launch("cudaMemsetAsync", e);
   eodm_bigram_prep_kernel<<<(unsigned)((NR + 255) / 256), 256, 0, st>>>(mask, NR, T, w.wv, w.cnt);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_prep_kernel", e);
-  eodm_bigram_split_px_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(px), w.wv, NR * (V / 4), V / 4, 1e-15f,
-                                                      reinterpret_cast<float4*>(w.E), reinterpret_cast<float4*>(w.Elo),
-                                                      reinterpret_cast<float4*>(w.Xa), reinterpret_cast<float4*>(w.Xalo));
+  if (V % 128 == 0)
+    eodm_bigram_split_px_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(px), w.wv, NR * (V / 4), V / 4, 1e-15f,
+                                                        reinterpret_cast<float4*>(w.E), reinterpret_cast<float4*>(w.Elo),
+                                                        reinterpret_cast<float4*>(w.Xa), reinterpret_cast<float4*>(w.Xalo));
+  else
+    eodm_bigram_split_px_pad_kernel<<<sms * 8, 256, 0, st>>>(px, w.wv, NR, V, vpad(V), 1e-15f, reinterpret_cast<float4*>(w.E),
+                                                            reinterpret_cast<float4*>(w.Elo), reinterpret_cast<float4*>(w.Xa),
+                                                            reinterpret_cast<float4*>(w.Xalo));
   if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_split_px_kernel", e);
   return EODM_OK;
 }
 
 extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B, int T, int V, float* C, float* N,
-                                     void* ws, void* stream) {
+                                     void* ws, void* stream) {   // V is re-bound to the padded width after the pre-pass
   int rc = bigram_check(px, mask, B, T, V, ws);
   if (rc != EODM_OK) return rc;
   if (!C) {
@@ -216,6 +275,10 @@ extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B
   const BigramWs w = carve(ws, NR, V);
   if ((rc = bigram_prep(px, mask, NR, T, V, w, sms, st)) != EODM_OK) return rc;
   if (N) eodm_bigram_n_kernel<<<1, 1, 0, st>>>(w.cnt, N);
+  // from here on everything has Vp columns; C itself when V is a multiple of 128, else the padded copy in the workspace
+  const int Vu = V;
+  V = vpad(Vu);
+  float* Cout = (V != Vu) ? w.CG : C;
   // C[u][v] = sum_r Xa[r][u] E[r+1][v]:  rows u, columns v, reduction over frames r; frame NR does not exist (reads 0)
   OperandMaps ma, mb;
   if ((rc = make_maps(&ma, w.Xa, w.Xalo, NR, V, V, true, eodm_tma::kTM)) != EODM_OK) return rc;
@@ -223,7 +286,7 @@ extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B
   eodm_tma::Args a;
   a.M = V; a.N = V; a.K = (int)NR;
   a.scale_out = nullptr;
-  a.C = C; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
+  a.C = Cout; a.ldc = V; a.c_row_shift = 0; a.accumulate = 0;
   a.m_tiles = (V + 255) / 256; a.n_tiles = (V + 255) / 256;   // 256 x 256 tiles, one per CTA pair
   // Tiles rarely divide over the CTA pairs (V=5120: 400 tiles over 74 pairs = 5.4 waves).  When the last wave is at
   // most half full its tiles are cut in two along the reduction: it then takes half a tile's time.  The second halves
@@ -232,22 +295,35 @@ extern "C" int eodm_bigram_dense_fwd(const float* px, const uint8_t* mask, int B
   const int rest = pairs > 0 ? tiles % pairs : 0;
   a.split_from = tiles;
   a.C2 = nullptr;
-  if (tiles > pairs && rest > 0 && 2 * rest <= pairs && NR >= 4096 && (((uintptr_t)C) & 15) == 0) {
+  if (tiles > pairs && rest > 0 && 2 * rest <= pairs && NR >= 4096 && (((uintptr_t)Cout) & 15) == 0) {
     a.split_from = tiles - rest;
     a.C2 = w.Glo;
   }
   cudaError_t e = eodm_tma::launch2<true, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st);
   if (e != cudaSuccess) return fail_launch("gemm3x_tma2_kernel", e);
   if (a.split_from < tiles) {
-    eodm_bigram_add_tiles_kernel<<<tiles - a.split_from, 256, 0, st>>>(C, w.Glo, V, a.n_tiles, a.split_from);
+    eodm_bigram_add_tiles_kernel<<<tiles - a.split_from, 256, 0, st>>>(Cout, w.Glo, V, a.n_tiles, a.split_from);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_add_tiles_kernel", e);
+  }
+  if (V != Vu) {
+    eodm_bigram_unpad_kernel<<<sms * 8, 256, 0, st>>>(Cout, Vu, Vu, V, C);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_unpad_kernel", e);
   }
   return EODM_OK;
 }
 
 // the two GEMMs of the VJP, given the operand planes of bigram_prep in the workspace
-static int bigram_bwd_core(long long NR, int V, const float* G, float* dpx, const BigramWs& w, int sms, cudaStream_t st) {
+static int bigram_bwd_core(long long NR, int Vu, const float* Gu, float* dpxu, const BigramWs& w, int sms, cudaStream_t st) {
   int rc;
+  const int V = vpad(Vu);
+  const float* G = Gu;
+  float* dpx = dpxu;
+  if (V != Vu) {   // padded mode: G is copied into a Vp x Vp matrix, the gradient is formed with Vp columns and copied out
+    eodm_bigram_pad_kernel<<<sms * 8, 256, 0, st>>>(Gu, Vu, V, w.CG);
+    if (cudaGetLastError() != cudaSuccess) return fail_launch("eodm_bigram_pad_kernel", cudaGetLastError());
+    G = w.CG;
+    dpx = w.dpxp;
+  }
   eodm_bigram_split_lo_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(G), (long long)V * (V / 4),
                                                       reinterpret_cast<float4*>(w.Glo));
   cudaError_t e = cudaGetLastError();
@@ -273,6 +349,10 @@ static int bigram_bwd_core(long long NR, int V, const float* G, float* dpx, cons
   a.split_from = a.m_tiles * a.n_tiles;
   if ((e = eodm_tma::launch2<false, true>(ma.x, ma.lo, mb.x, mb.lo, a, sms, st)) != cudaSuccess)
     return fail_launch("gemm3x_tma2_kernel", e);
+  if (V != Vu) {
+    eodm_bigram_unpad_kernel<<<sms * 8, 256, 0, st>>>(dpx, NR, Vu, V, dpxu);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail_launch("eodm_bigram_unpad_kernel", e);
+  }
   return EODM_OK;
 }
 
@@ -281,11 +361,11 @@ static int bigram_bwd_args(int B, int T, int V, const float* G, const float* dpx
     eodm_set_error("null pointer");
     return EODM_EINVAL;
   }
-  if (B < 1 || T < 2 || V < 128 || (V % 128) != 0) {
-    eodm_set_error("bad shape B=%d T=%d V=%d (V a multiple of 128, T >= 2)", B, T, V);
+  if (B < 1 || T < 2 || V < 2) {
+    eodm_set_error("bad shape B=%d T=%d V=%d (V >= 2, T >= 2)", B, T, V);
     return EODM_ESHAPE;
   }
-  if ((((uintptr_t)G | (uintptr_t)dpx) & 15) != 0) {
+  if ((V % 128) == 0 && (((uintptr_t)G | (uintptr_t)dpx) & 15) != 0) {
     eodm_set_error("G and dpx must be 16-byte aligned");
     return EODM_EINVAL;
   }

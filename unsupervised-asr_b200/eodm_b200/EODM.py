@@ -365,7 +365,7 @@ def EODM_loss(_logits, mask, conv_op, k, py):
 # ---------------------------------------------------------------------------
 def bigram_dense_fwd(px, mask, return_ws=False):
     """C[u, v] = sum_{b, t<=T-2} mask[b,t] (px[b,t,u]+eps)(px[b,t+1,v]+eps), f32[V, V]; N = sum(mask).
-    V must be a multiple of 128.  return_ws: also return the workspace, whose operand planes bigram_dense_bwd can
+    Any V >= 2 (a V that is not a multiple of 128 is padded inside the workspace).  return_ws: also return the workspace, whose operand planes bigram_dense_bwd can
     reuse (`ws=`) as long as px and mask are the same."""
     px = _f32c(px, "px")
     B, T, V = px.shape
@@ -427,7 +427,7 @@ class _DenseBigramLossFn(torch.autograd.Function):
 
 
 def EODM_loss_dense_bigram(_logits, mask, conv_op, k, py):
-    """EODM_loss (models/EODM.py:5-25) for a kernel_size-2 table over a large vocabulary (V a multiple of 128):
+    """EODM_loss (models/EODM.py:5-25) for a kernel_size-2 table over a large vocabulary (any V; padded to a multiple of 128 inside):
     the expected counts of ALL bigrams come from one tensor-core contraction, the K prior entries are gathered
     from it.  Same arguments and result as EODM_loss."""
     if not isinstance(conv_op, PNgram):
