@@ -603,7 +603,11 @@ def test_dense_bigram_loss_at_hkust_vocabulary(eodm):
 
 @pytest.mark.parametrize("V,n,K,B,T", [(64, 3, 60000, 3, 70),      # K too large for shared-memory accumulators
                                        (800, 2, 5000, 2, 45),      # wide vocabulary: one window per lane (the walk's limit is V ~ 830)
-                                       (300, 3, 4000, 2, 50)])
+                                       (300, 3, 4000, 2, 50),
+                                       (1000, 3, 5000, 2, 40),     # beyond it: tiles of 16 rows (half the lanes own a window)
+                                       (2000, 3, 4000, 2, 30),     # 8 rows
+                                       (3674, 3, 3000, 1, 20),     # 4 rows: the character inventory of hkust_char_CTC.yaml:17
+                                       (3000, 2, 3000, 2, 11)])
 def test_resource_fallbacks_vs_oracle(eodm, V, n, K, B, T):
     """Shapes that leave the default resource plan: global-memory accumulators, narrow tiles."""
     ids, py = eodm.synth.table(V, n, K, seed=V)
@@ -619,16 +623,16 @@ def test_resource_fallbacks_vs_oracle(eodm, V, n, K, B, T):
 
 
 def test_unsupported_shape_is_reported(eodm):
-    ids, py = eodm.synth.table(6000, 2, 100, seed=1)
-    table = eodm.NgramTable.from_ids(ids, 6000, device=0)
-    px = torch.full((1, 8, 6000), 1.0 / 6000, device=_dev())
+    ids, py = eodm.synth.table(12000, 2, 100, seed=1)
+    table = eodm.NgramTable.from_ids(ids, 12000, device=0)
+    px = torch.full((1, 8, 12000), 1.0 / 12000, device=_dev())
     with pytest.raises(eodm.EodmError) as e:
         eodm.counts_fwd(table, px, torch.ones(1, 8, dtype=torch.bool, device=_dev()))
     assert e.value.status == -5 and "shared memory" in str(e.value)
-    # V = 1000 still fits the forward tile but not the backward one (px tile + dpx tile): reported, not mis-computed
-    ids, py = eodm.synth.table(1000, 2, 100, seed=1)
-    table = eodm.NgramTable.from_ids(ids, 1000, device=0)
-    px = torch.full((1, 8, 1000), 1.0 / 1000, device=_dev())
+    # V = 6000 still fits a forward tile (4 rows) but not the backward one (px tile + dpx tile): reported, not mis-computed
+    ids, py = eodm.synth.table(6000, 2, 100, seed=1)
+    table = eodm.NgramTable.from_ids(ids, 6000, device=0)
+    px = torch.full((1, 8, 6000), 1.0 / 6000, device=_dev())
     m = torch.ones(1, 8, dtype=torch.bool, device=_dev())
     eodm.counts_fwd(table, px, m)
     with pytest.raises(eodm.EodmError) as e:

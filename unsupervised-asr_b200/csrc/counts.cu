@@ -259,11 +259,14 @@ __device__ __forceinline__ void fwd_visit(FwdWalk& w, const TrieArg& tr, const f
 template <int DEPTH, int R, bool ACC_SMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restrict__ px,
-                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int n_tiles,
+                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int tsa, int n_tiles,
                        int n_leaves, float* __restrict__ part, int* __restrict__ part_cnt) {
   constexpr int TS = 32 * R;
   extern __shared__ float smem[];
-  const int ld = odd_ld(TS + n - 1);
+  // tsa = tile rows the shared-memory layout is cut for: TS, or (R = 1, wide vocabularies) 16 / 8 / 4 -- then only the
+  // first tsa lanes own windows; the others read past their phone's row (finite values of the next row or of the arrays
+  // behind the tile) under a zero window mask, and never write
+  const int ld = odd_ld(tsa + n - 1);
   float* Ps = smem;                                   // [V][ld]
   float* wm = Ps + V * ld;                            // [TS]
   float* stage = wm + TS;                             // [kWarps][kStageLeaves][kStageLd]
@@ -287,7 +290,7 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * ts;
     __syncthreads();  // the previous tile is fully consumed (and acc / s_cnt are initialised)
-    stage_tile(Ps, ld, px, row0, ts + n - 1, TS + n - 1, NR, V);
+    stage_tile(Ps, ld, px, row0, ts + n - 1, tsa + n - 1, NR, V);
     int my_valid = 0;
     for (int i = threadIdx.x; i < TS; i += kThreads) {   // warp-uniform trip count: TS is a multiple of 32
       const long long row = row0 + i;
@@ -507,12 +510,12 @@ __device__ __forceinline__ void bwd_visit(BwdWalk& w, const int (&off)[EODM_MAX_
 template <int DEPTH, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __restrict__ px,
-                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int n_tiles,
+                       const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int tsa, int n_tiles,
                        float* __restrict__ dpx, int accumulate) {
   constexpr int TS = 32 * R;
   extern __shared__ float smem[];
-  const int ld = odd_ld(TS + 2 * (n - 1));
-  const int ldo = odd_ld(TS);
+  const int ld = odd_ld(tsa + 2 * (n - 1));   // tsa: see eodm_counts_fwd_kernel
+  const int ldo = odd_ld(tsa);
   float* Ps = smem;                       // [V][ld]   rows row0-(n-1) .. row0+ts+n-2
   float* dP = Ps + V * ld;                // [V][ldo]
   float* wm = dP + V * ldo;               // [TS+n-1]  windows row0-(n-1) .. row0+TS-1
@@ -535,7 +538,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * ts;
     __syncthreads();
-    stage_tile(Ps, ld, px, row0 - (n - 1), ts + 2 * (n - 1), TS + 2 * (n - 1), NR, V);
+    stage_tile(Ps, ld, px, row0 - (n - 1), ts + 2 * (n - 1), tsa + 2 * (n - 1), NR, V);
     for (int i = threadIdx.x; i < V * ldo; i += kThreads) dP[i] = 0.f;
     int my_valid = 0;
     for (int i = threadIdx.x; i < TS + n - 1; i += kThreads) {
@@ -565,8 +568,10 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
         auto flush = [&](bool complete) {
           if (complete) {
             float* d = dP + cur_root * ldo + lane;
+            if (R > 1 || lane < tsa) {   // narrow tiles: lanes beyond the tile own no row of dP
 #pragma unroll
-            for (int r = 0; r < R; ++r) d[32 * r] += acc[r] * wmv[r];
+              for (int r = 0; r < R; ++r) d[32 * r] += acc[r] * wmv[r];
+            }
           } else {
             float* d = side + (warp * 2 + n_side) * TS + lane;
 #pragma unroll
@@ -605,7 +610,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
         }
         __syncthreads();
         // roots shared between neighbouring warps: add their partial sums in warp order
-        for (int i = threadIdx.x; i < TS; i += kThreads) {
+        for (int i = threadIdx.x; i < tsa; i += kThreads) {
 #pragma unroll 1
           for (int s = 0; s < 2 * kWarps; ++s) {
             const int root = side_root[s >> 1][s & 1];
@@ -646,14 +651,16 @@ __global__ void __launch_bounds__(256) eodm_prepare_g_kernel(const float* __rest
 
 constexpr int kMaxSmem = 227 * 1024;
 
-size_t fwd_smem_bytes(int R, int V, int n, int n_leaves, bool acc_smem) {
+size_t fwd_smem_bytes(int R, int V, int n, int n_leaves, bool acc_smem, int tsa = 0) {
   const int TS = 32 * R;
-  return sizeof(float) * ((size_t)V * odd_ld(TS + n - 1) + TS + (size_t)kWarps * kStageLeaves * kStageLd +
+  if (tsa <= 0) tsa = TS;
+  return sizeof(float) * ((size_t)V * odd_ld(tsa + n - 1) + TS + (size_t)kWarps * kStageLeaves * kStageLd +
                           (acc_smem ? n_leaves : 0));
 }
-size_t bwd_smem_bytes(int R, int V, int n) {
+size_t bwd_smem_bytes(int R, int V, int n, int tsa = 0) {
   const int TS = 32 * R;
-  return sizeof(float) * ((size_t)V * odd_ld(TS + 2 * (n - 1)) + (size_t)V * odd_ld(TS) + (TS + n - 1) +
+  if (tsa <= 0) tsa = TS;
+  return sizeof(float) * ((size_t)V * odd_ld(tsa + 2 * (n - 1)) + (size_t)V * odd_ld(tsa) + (TS + n - 1) +
                           (size_t)kWarps * 2 * TS);
 }
 
@@ -663,29 +670,42 @@ __host__ inline bool r_allowed(int depth, int R) { return R <= 8 || depth <= 5; 
 
 // Tile height: the smallest number of equal row slices per SM such that a slice fits the lanes.
 struct Tiling {
-  int R, ts, n_tiles, grid;
+  int R, ts, tsa, n_tiles, grid;   // tsa: tile rows the shared-memory layout is cut for (32 R, or 16 / 8 / 4 with R = 1)
 };
 int g_force_R = 0, g_force_ts = 0;  // test hook (eodm_debug_set_tiling): 0 = choose automatically
 constexpr int kMinTileRows = 128;   // a tile costs a full trie walk whatever its height: do not cut finer
 
 template <typename FitFn>
-bool choose_tiling(const eodm_table* t, long long NR, FitFn fits, Tiling* out) {
+bool choose_tiling(const eodm_table* t, long long NR, FitFn fits, Tiling* out, bool allow_narrow = true) {
   int Rmax = 0;
   for (int R : kRs)
     if (r_allowed(t->n, R) && fits(R) && (!g_force_R || R <= g_force_R)) {
       Rmax = R;
       break;
     }
-  if (!Rmax) return false;
+  // wide vocabularies: not even one window per lane fits -- narrow tiles of 16, 8 or 4 rows on the R = 1 kernels (a
+  // quarter to an eighth of the lanes work: a path for V up to ~4000 at n = 3, not a fast one)
+  int tsa = 0;
+  if (!Rmax) {
+    if (!allow_narrow) return false;
+    for (int cand : {16, 8, 4})
+      if (fits(-cand)) {
+        tsa = cand;
+        break;
+      }
+    if (!tsa) return false;
+    Rmax = 1;
+  }
   const long long sms = t->sm_count;
   long long ts = 0;
+  const long long cap = tsa ? tsa : 32LL * Rmax;
   for (long long k = 1;; ++k) {
     ts = (NR + sms * k - 1) / (sms * k);
-    if (ts <= 32LL * Rmax) break;
+    if (ts <= cap) break;
   }
-  if (ts < kMinTileRows) ts = kMinTileRows < 32LL * Rmax ? kMinTileRows : 32LL * Rmax;
+  if (ts < kMinTileRows) ts = kMinTileRows < cap ? kMinTileRows : cap;
   if (ts > NR) ts = NR;
-  if (g_force_ts > 0 && g_force_ts <= 32 * Rmax) ts = g_force_ts;
+  if (g_force_ts > 0 && g_force_ts <= cap) ts = g_force_ts;
   if (ts < 1) ts = 1;
   int R = Rmax;
   for (int cand : kRs)
@@ -693,6 +713,7 @@ bool choose_tiling(const eodm_table* t, long long NR, FitFn fits, Tiling* out) {
   if (g_force_R && g_force_R <= Rmax) R = g_force_R;
   const long long n_tiles = (NR + ts - 1) / ts;
   out->R = R;
+  out->tsa = tsa ? tsa : 32 * R;
   out->ts = (int)ts;
   out->n_tiles = (int)n_tiles;
   out->grid = (int)(n_tiles < sms ? n_tiles : sms);
@@ -711,12 +732,12 @@ cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mas
       auto k = eodm_counts_fwd_kernel<DEPTH, R, true>;
       e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, n_leaves, part, part_cnt);
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt);
     } else {
       auto k = eodm_counts_fwd_kernel<DEPTH, R, false>;
       e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, n_leaves, part, part_cnt);
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt);
     }
     return cudaGetLastError();
   }
@@ -731,7 +752,7 @@ cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask
     auto k = eodm_counts_bwd_kernel<DEPTH, R>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.n_tiles, dpx, accumulate);
+    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, dpx, accumulate);
     return cudaGetLastError();
   }
 }
@@ -795,17 +816,18 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   const int n_leaves = t->trie[0].n_leaves;
   bool acc_smem = true;
   Tiling tl;
-  auto fits_s = [&](int R) { return fwd_smem_bytes(R, V, n, n_leaves, true) <= (size_t)kMaxSmem; };
-  auto fits_g = [&](int R) { return fwd_smem_bytes(R, V, n, n_leaves, false) <= (size_t)kMaxSmem; };
+  // a negative argument asks for a narrow tile of -R rows on the R = 1 kernel
+  auto fits_s = [&](int R) { return fwd_smem_bytes(R < 0 ? 1 : R, V, n, n_leaves, true, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
+  auto fits_g = [&](int R) { return fwd_smem_bytes(R < 0 ? 1 : R, V, n, n_leaves, false, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
   // prefer shared-memory accumulators unless they force a much smaller tile than global ones would allow
-  if (!choose_tiling(t, NR, fits_s, &tl)) {
+  if (!choose_tiling(t, NR, fits_s, &tl, false)) {
     acc_smem = false;
     if (!choose_tiling(t, NR, fits_g, &tl)) {
-      eodm_set_error("trie path: a [V=%d] x 32-row tile does not fit in %d bytes of shared memory", V, kMaxSmem);
+      eodm_set_error("trie path: not even a [V=%d] x 4-row tile fits in %d bytes of shared memory", V, kMaxSmem);
       return EODM_EUNSUPPORTED;
     }
   }
-  const size_t smem = fwd_smem_bytes(tl.R, V, n, n_leaves, acc_smem);
+  const size_t smem = fwd_smem_bytes(tl.R, V, n, n_leaves, acc_smem, tl.tsa);
   float *part, *g;
   int* cnt;
   uint2* ng;
@@ -847,12 +869,12 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   Tiling tl;
-  auto fits = [&](int R) { return bwd_smem_bytes(R, V, n) <= (size_t)kMaxSmem; };
+  auto fits = [&](int R) { return bwd_smem_bytes(R < 0 ? 1 : R, V, n, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
   if (!choose_tiling(t, NR, fits, &tl)) {
-    eodm_set_error("trie path: a [V=%d] x 32-row tile does not fit in %d bytes of shared memory", V, kMaxSmem);
+    eodm_set_error("trie path: not even a [V=%d] x 4-row tile fits in %d bytes of shared memory", V, kMaxSmem);
     return EODM_EUNSUPPORTED;
   }
-  const size_t smem = bwd_smem_bytes(tl.R, V, n);
+  const size_t smem = bwd_smem_bytes(tl.R, V, n, tl.tsa);
   float *part, *g;
   int* cnt;
   uint2* ng;
