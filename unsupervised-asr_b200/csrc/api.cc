@@ -365,6 +365,7 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->gS, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
   if (e == cudaSuccess) e = cudaMalloc(&s->ws, eodm_workspace_bytes(t, maxB, maxT));
+  if (e == cudaSuccess) e = cudaMemset(s->ws, 0, eodm_workspace_bytes(t, maxB, maxT));   // the tail kernel's ticket starts at 0
   if (e == cudaSuccess) e = cudaMemcpy(s->py, py_host, (size_t)t->K * sizeof(float), cudaMemcpyHostToDevice);
   if (prev >= 0) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -387,14 +388,32 @@ extern "C" int eodm_session_set_peer(eodm_session* s, eodm_peer* peer) {
 }
 
 // exchange (if any) + loss + dloss/dS from this rank's packed counts
+static void* session_tcb_ws(const eodm_session* s) { return (char*)s->ws + counts_ws_aligned(s->t) + tc_ws_aligned(s->t); }
+static void* session_tcf_ws(const eodm_session* s) { return (char*)session_tcb_ws(s) + tcb_ws_aligned(s->t); }
+
+// *image_ready: the tensor-core VJP's G image was written along with the loss (eodm_tc_tail_launch) -- the VJP launches of
+// this step then skip their own image kernel (session_vjp below)
 static int session_exchange_and_loss(eodm_session* s, float* counts, void* comm, float* loss, bool need_grad,
-                                     cudaStream_t st) {
+                                     cudaStream_t st, bool* image_ready) {
   const int K = s->t->K;
+  *image_ready = false;
   if (s->peer) return eodm_peer_loss(s->peer, counts, s->py, 1e-15f, loss, need_grad ? s->gS : nullptr, nullptr, st);
   int rc = EODM_OK;
   if (comm) rc = eodm_allreduce_counts(comm, counts, K, counts + K, st);
-  if (rc == EODM_OK) rc = eodm_loss_launch(counts, counts + K, s->py, K, 1e-15f, loss, need_grad ? s->gS : nullptr, st);
-  return rc;
+  if (rc != EODM_OK) return rc;
+  if (need_grad && use_tensor_bwd(s->t) && s->t->d_ids) {
+    *image_ready = true;
+    return eodm_tc_tail_launch(s->t, nullptr, counts, counts + K, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st);
+  }
+  return eodm_loss_launch(counts, counts + K, s->py, K, 1e-15f, loss, need_grad ? s->gS : nullptr, st);
+}
+
+static int session_vjp(eodm_session* s, const float* px, const uint8_t* mask, int B, int T, float* dpx, cudaStream_t st,
+                       bool image_ready) {
+  if (!image_ready) return eodm_counts_bwd(s->t, px, mask, B, T, s->gS, dpx, s->ws, st);
+  const int rc = check_batch(s->t, px, mask, B, T);
+  if (rc != EODM_OK) return rc;
+  return eodm_tcb_launch(s->t, px, mask, B, T, s->gS, dpx, session_tcb_ws(s), st, 0, 1);
 }
 
 extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, const uint8_t* mask, int B, int T,
@@ -409,9 +428,20 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   float* S = s->counts;
   float* N = s->counts + t->K;
   int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
-  if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);
-  if (rc == EODM_OK) rc = session_exchange_and_loss(s, s->counts, comm, loss, dlogits != nullptr, st);
-  if (rc == EODM_OK && dlogits) rc = eodm_counts_bwd(t, s->px, mask, B, T, s->gS, s->dpx, s->ws, st);
+  bool image_ready = false;
+  if (rc == EODM_OK && dlogits && !comm && !s->peer && fwd_path(t) == 3 && use_tensor_bwd(t)) {
+    // both counts kernels on the tensor cores and nothing to exchange: what lies between them -- the forward's slice sums,
+    // the loss, dloss/dS, the VJP's G image -- is one launch
+    EodmTcfParts parts;
+    rc = check_batch(t, s->px, mask, B, T);
+    if (rc == EODM_OK) rc = eodm_tcf_launch_main(t, s->px, mask, B, T, session_tcf_ws(s), st, &parts);
+    if (rc == EODM_OK) rc = eodm_tc_tail_launch(t, &parts, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st);
+    image_ready = true;
+  } else {
+    if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);
+    if (rc == EODM_OK) rc = session_exchange_and_loss(s, s->counts, comm, loss, dlogits != nullptr, st, &image_ready);
+  }
+  if (rc == EODM_OK && dlogits) rc = session_vjp(s, s->px, mask, B, T, s->dpx, st, image_ready);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(s->px, s->dpx, rows, t->V, dlogits, st);
   return rc;
 }
@@ -444,15 +474,16 @@ static int session_loss_pipelined(eodm_session* s, const float* logits_host, con
     if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
   }
   if (e == cudaSuccess && rc == EODM_OK) rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  bool image_ready = false;
   if (e == cudaSuccess && rc == EODM_OK)
-    rc = session_exchange_and_loss(s, s->counts, comm, s->loss, dlogits_host != nullptr, s->st);
+    rc = session_exchange_and_loss(s, s->counts, comm, s->loss, dlogits_host != nullptr, s->st, &image_ready);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(s->ev_done, s->st);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->copy_st, s->ev_done, 0);
   if (e == cudaSuccess && rc == EODM_OK)
     e = cudaMemcpyAsync(loss_host, s->loss, sizeof(float), cudaMemcpyDeviceToHost, s->copy_st);
   for (int c = 0; c < 2 && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
     const size_t rows = (size_t)Bc[c] * T;
-    rc = eodm_counts_bwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, s->gS, s->dpx + row0[c] * V, s->ws, s->st);
+    rc = session_vjp(s, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, s->dpx + row0[c] * V, s->st, image_ready);
     if (rc == EODM_OK)
       rc = eodm_softmax_bwd_launch(s->px + row0[c] * V, s->dpx + row0[c] * V, (int64_t)rows, V, s->dlogits + row0[c] * V,
                                    s->st);
@@ -564,15 +595,16 @@ extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logit
   }
   if (e == cudaSuccess && rc == EODM_OK && nch == 2)
     rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  bool image_ready = false;
   if (e == cudaSuccess && rc == EODM_OK)
-    rc = session_exchange_and_loss(s, s->counts, comm, sl.loss, dlogits_host != nullptr, s->st);
+    rc = session_exchange_and_loss(s, s->counts, comm, sl.loss, dlogits_host != nullptr, s->st, &image_ready);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaEventRecord(sl.loss_ready, s->st);
   if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->d2h_st, sl.loss_ready, 0);
   if (e == cudaSuccess && rc == EODM_OK)
     e = cudaMemcpyAsync(loss_host, sl.loss, sizeof(float), cudaMemcpyDeviceToHost, s->d2h_st);
   for (int c = 0; c < nch && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
     const size_t rows = (size_t)Bc[c] * T;
-    rc = eodm_counts_bwd(t, s->px + row0[c] * V, sl.mask + row0[c], Bc[c], T, s->gS, s->dpx + row0[c] * V, s->ws, s->st);
+    rc = session_vjp(s, s->px + row0[c] * V, sl.mask + row0[c], Bc[c], T, s->dpx + row0[c] * V, s->st, image_ready);
     if (rc == EODM_OK)
       rc = eodm_softmax_bwd_launch(s->px + row0[c] * V, s->dpx + row0[c] * V, (int64_t)rows, V, sl.dlogits + row0[c] * V, s->st);
     if (rc != EODM_OK) break;

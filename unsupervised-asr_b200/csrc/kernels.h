@@ -26,13 +26,27 @@ bool eodm_tcf_supported(const eodm_table* t);
 size_t eodm_tcf_workspace_bytes(const eodm_table* t);
 int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N, void* ws,
                     cudaStream_t st);
+// the main kernel only: per-slice partial sums and frame counts, for the fused tail (eodm_tc_tail_launch)
+struct EodmTcfParts {
+  const float* partS;     // [n_slices][slice_stride]; entry ((a * vp) + b) * vp + c of a slice is trigram (a, b, c)
+  const int* partN;       // [n_slices] valid frames
+  int n_slices, vp;
+  long long slice_stride;
+};
+int eodm_tcf_launch_main(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, void* ws, cudaStream_t st,
+                         EodmTcfParts* parts);
 
 // tcbwd.cu -- tcgen05 VJP for trigram-only tables over V <= 64
 int eodm_tcb_vp(int n, int V, bool full_order);   // padded vocabulary the path would use, 0 = not applicable
 bool eodm_tcb_supported(const eodm_table* t);
 size_t eodm_tcb_workspace_bytes(const eodm_table* t);
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
-                    void* ws, cudaStream_t st, int accumulate = 0);
+                    void* ws, cudaStream_t st, int accumulate = 0, int image_ready = 0);
+// The step between the two tensor-core kernels as ONE launch: S and N (from the forward's per-slice partials when `parts`
+// is given, else read from S_io / N_io -- e.g. after an all-reduce), loss, dloss/dS, and the G image the VJP kernel reads
+// (then eodm_tcb_launch(..., image_ready = 1)).  Loss bits equal eodm_loss_launch's.
+int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S_io, float* N_io, const float* py, float eps,
+                        float* loss, float* gS, void* ws_tcb, cudaStream_t st);
 
 // ops.cu -- loss, softmax, materialising op
 int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,

@@ -588,6 +588,108 @@ __global__ void __launch_bounds__(256) eodm_tcb_image_kernel(const float* __rest
   img[kstep * 2048 + 1024 + in] = tf32_lo(g);
 }
 
+// ---- the step between the forward and the VJP as one launch (replaces the forward's finish kernel, eodm_loss_kernel and
+//      eodm_tcb_image_kernel: 9 + 12 + 4 us of a 400 us step at timit_c2).  Thread = element of the G image: it forms the
+//      count of its trigram (the forward's slices added in slice order, as the finish kernel does), the loss term and
+//      dloss/dS of every table entry that is this trigram, and writes the image's hi / remainder words.  The block that
+//      finishes last adds the K loss terms in the order of eodm_loss_kernel (1024 strided partial sums, the same two
+//      shuffle trees), so the loss has the same bits whichever path produced it.  No float atomics.
+struct TailArgs {
+  const float* partS;      // forward partials, or nullptr: read S
+  const int* partN;
+  int n_slices, vp;
+  long long slice_stride;
+  float* S;                // [K] written (partials) or read
+  float* N;                // [1]
+  const float* py;
+  const int32_t* ids;      // [K][3]
+  const int32_t* zmap;
+  const int32_t* next_dup;
+  long long zmap_len;
+  int K;
+  float eps;
+  float* gS;               // [K]
+  float* term;             // [K] scratch: loss terms
+  float* img;
+  float* loss;
+  unsigned* done;
+};
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant__ TailArgs a) {
+  __shared__ float n_s;
+  __shared__ unsigned last;
+  __shared__ float red[32];
+  if (threadIdx.x == 0) {
+    float n;
+    if (a.partS) {
+      int c = 0;
+      for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
+      n = (float)c;
+      if (blockIdx.x == 0) a.N[0] = n;
+    } else {
+      n = a.N[0];
+    }
+    n_s = n;
+  }
+  __syncthreads();
+  const float n = n_s;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.zmap_len) {
+    float g = 0.f;
+    int z = a.zmap[i];
+    if (z >= 0) {
+      float s;
+      if (a.partS) {
+        const float* p = a.partS + ((size_t)a.ids[3 * z] * a.vp + a.ids[3 * z + 1]) * a.vp + a.ids[3 * z + 2];
+        s = 0.f;
+        for (int sl = 0; sl < a.n_slices; ++sl) s += p[(size_t)sl * a.slice_stride];
+      }
+      for (; z >= 0; z = a.next_dup[z]) {   // duplicates of a trigram share its count; their gradients add up in table order
+        if (a.partS) a.S[z] = s;
+        else s = a.S[z];
+        const float pz = s / n, p = a.py[z];
+        a.term[z] = -p * logf(pz + a.eps);
+        const float gz = -p / (pz + a.eps) / n;
+        a.gS[z] = gz;
+        g += gz;
+      }
+    }
+    const long long kstep = i >> 10, in = i & 1023;
+    a.img[kstep * 2048 + in] = g;
+    a.img[kstep * 2048 + 1024 + in] = tf32_lo(g);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // eodm_loss_kernel's order: virtual thread t = 0..1023 adds term[t], term[t + 1024], ...; warps of 32 consecutive t are
+  // reduced by the xor tree, then the 32 warp sums by the same tree
+  const volatile float* term = a.term;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float acc = 0.f;
+    for (int z = threadIdx.x + 256 * q; z < a.K; z += 1024) acc += term[z];
+    acc = warp_sum_t(acc);
+    if ((threadIdx.x & 31) == 0) red[8 * q + (threadIdx.x >> 5)] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const float v = warp_sum_t(red[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      a.loss[0] = v;
+      *a.done = 0;   // ready for the next step (graph replays included)
+    }
+  }
+}
+
 template <int VP, bool PROF = false>
 cudaError_t launch_vp(const CUtensorMap& tg, const CUtensorMap& tp, const BArgs& a, int sm_count, cudaStream_t st) {
   auto k = eodm_tc_bwd_kernel<VP, PROF>;
@@ -619,13 +721,50 @@ int eodm_tcb_vp(int n, int V, bool full_order) {
 
 bool eodm_tcb_supported(const eodm_table* t) { return t->tcb.vp > 0 && t->tcb.d_zmap != nullptr; }
 
+// workspace: [G image: zmap_len x (hi, remainder) f32, 1 KiB aligned][loss terms: K f32][ticket of the tail kernel]
 size_t eodm_tcb_workspace_bytes(const eodm_table* t) {
   if (!eodm_tcb_supported(t)) return 0;
-  return (size_t)t->tcb.zmap_len * 2 * sizeof(float) + 1024;
+  return (size_t)t->tcb.zmap_len * 2 * sizeof(float) + (size_t)t->K * sizeof(float) + 1024 + 512;
+}
+
+int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S_io, float* N_io, const float* py, float eps,
+                        float* loss, float* gS, void* ws_tcb, cudaStream_t st) {
+  if (!eodm_tcb_supported(t) || !t->d_ids) {
+    eodm_set_error("fused tail needs a trigram-only table over V <= 48");
+    return EODM_EUNSUPPORTED;
+  }
+  TailArgs a;
+  a.partS = parts ? parts->partS : nullptr;
+  a.partN = parts ? parts->partN : nullptr;
+  a.n_slices = parts ? parts->n_slices : 0;
+  a.vp = parts ? parts->vp : 0;
+  a.slice_stride = parts ? parts->slice_stride : 0;
+  a.S = S_io;
+  a.N = N_io;
+  a.py = py;
+  a.ids = t->d_ids;
+  a.zmap = t->tcb.d_zmap;
+  a.next_dup = t->tcb.d_next;
+  a.zmap_len = t->tcb.zmap_len;
+  a.K = t->K;
+  a.eps = eps;
+  a.gS = gS;
+  a.img = (float*)(((uintptr_t)ws_tcb + 1023) & ~(uintptr_t)1023);
+  a.term = a.img + (size_t)t->tcb.zmap_len * 2;
+  a.done = (unsigned*)(a.term + t->K);
+  a.loss = loss;
+  // the ticket word must be zero at the first launch (sessions zero their workspace once); the kernel leaves it zero
+  eodm_tc_tail_kernel<<<(unsigned)((a.zmap_len + 255) / 256), 256, 0, st>>>(a);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_tc_tail_kernel launch failed: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
 }
 
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
-                    void* ws, cudaStream_t st, int accumulate) {
+                    void* ws, cudaStream_t st, int accumulate, int image_ready) {
   if (!eodm_tcb_supported(t)) {
     eodm_set_error("tensor-core VJP needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -633,7 +772,7 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   const long long NR = (long long)B * T;
   float* img = (float*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   const long long n = t->tcb.zmap_len;
-  eodm_tcb_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gS, t->tcb.d_zmap, t->tcb.d_next, n, img);
+  if (!image_ready) eodm_tcb_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gS, t->tcb.d_zmap, t->tcb.d_next, n, img);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_tcb_image_kernel launch failed: %s", cudaGetErrorString(e));

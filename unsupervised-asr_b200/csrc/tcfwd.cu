@@ -68,6 +68,7 @@ struct FArgs {
   const float* px;
   const uint8_t* mask;
   float* partS;            // [n_slices][2304][48]
+  int* partN;              // [n_slices] valid frames of every slice (written by the slice's first CTA), for the fused tail
   long long NR, rows_per_slice;
   int T, V, n_slices;
   int bulk;                // 1: posterior tiles arrive by cp.async.bulk (V % 4 == 0, px 16-byte aligned), 0: by loads
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       return q >= kVP / 4 ? q - kVP / 4 : q;
     };
     __shared__ __align__(16) float ok_s[2][kTile];
+    __shared__ int n_frames;
+    int my_frames = 0;
     float* raw = tile0 + 2 * kTileFloats;
     auto issue_raw = [&](int k) {
       const long long st0 = w_begin + (long long)k * kTile;
@@ -225,7 +228,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       {
         const long long wrow = st0 + t128;
         float ok = 0.f;
-        if (wrow < w_end) ok = ((int)(wrow % a.T) <= a.T - 3 && __ldg(a.mask + wrow) != 0) ? 1.f : 0.f;
+        if (wrow < w_end) {
+          const bool m = __ldg(a.mask + wrow) != 0;
+          my_frames += m;                                   // N counts every valid frame (models/EODM.py:20)
+          ok = (m && (int)(wrow % a.T) <= a.T - 3) ? 1.f : 0.f;
+        }
         ok_s[buf][t128] = ok;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -314,6 +321,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       fence_async_smem();   // the B tile is read by the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.pt_full[buf]);
+    }
+    if (mg == 0 && a.partN) {   // integer count: exact and order-independent
+      if (t128 == 0) n_frames = 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      my_frames = __reduce_add_sync(0xffffffffu, my_frames);
+      if (lane == 0 && my_frames) atomicAdd(&n_frames, my_frames);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t128 == 0) a.partN[slice] = n_frames;
     }
   } else {
     // ------------------------------------------------------------------ A producers: warpgroup g = M tile g, thread = pair row
@@ -447,11 +462,13 @@ bool eodm_tcf_supported(const eodm_table* t) {
 
 size_t eodm_tcf_workspace_bytes(const eodm_table* t) {
   if (!eodm_tcf_supported(t)) return 0;
-  return sizeof(float) * (size_t)slices_for(t) * (kMTiles * 128) * kVP + 256;
+  return sizeof(float) * (size_t)slices_for(t) * (kMTiles * 128) * kVP + sizeof(int) * (size_t)slices_for(t) + 512;
 }
 
-int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N, void* ws,
-                    cudaStream_t st) {
+// The main kernel alone: per-slice partial sums partS[slice][a 48 + b][c] and per-slice frame counts.  What turns them into
+// S and N is either eodm_tc_fwd3_finish_kernel (below) or the fused tail of tcbwd.cu.
+int eodm_tcf_launch_main(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, void* ws, cudaStream_t st,
+                         EodmTcfParts* parts) {
   if (!eodm_tcf_supported(t)) {
     eodm_set_error("tensor-core forward needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -461,6 +478,7 @@ int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   a.px = px;
   a.mask = mask;
   a.partS = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  a.partN = (int*)(a.partS + (size_t)slices_for(t) * (kMTiles * 128) * kVP);
   a.NR = NR;
   a.T = T;
   a.V = t->V;
@@ -481,8 +499,22 @@ int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
     eodm_set_error("eodm_tc_fwd3_kernel launch failed: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
   }
-  eodm_tc_fwd3_finish_kernel<<<(t->K + 255) / 256, 256, 0, st>>>(a.partS, n_slices, t->d_ids, t->K, mask, NR, S, N);
-  e = cudaGetLastError();
+  parts->partS = a.partS;
+  parts->partN = a.partN;
+  parts->n_slices = n_slices;
+  parts->slice_stride = (long long)(kMTiles * 128) * kVP;
+  parts->vp = kVP;
+  return EODM_OK;
+}
+
+int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N, void* ws,
+                    cudaStream_t st) {
+  EodmTcfParts parts;
+  const int rc = eodm_tcf_launch_main(t, px, mask, B, T, ws, st, &parts);
+  if (rc != EODM_OK) return rc;
+  const long long NR = (long long)B * T;
+  eodm_tc_fwd3_finish_kernel<<<(t->K + 255) / 256, 256, 0, st>>>(parts.partS, parts.n_slices, t->d_ids, t->K, mask, NR, S, N);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_tc_fwd3_finish_kernel launch failed: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
