@@ -491,8 +491,12 @@ def main():
                "sample": r["sample"] + "; 1 warm-up + best of 3 (%.2f s)" % best}
 
     if rank == 0:
-        # softmax, counts fwd, finish, loss (or the fused exchange+loss), G image (or prepare_g), VJP, softmax VJP
-        launches_per_step = 7
+        # our kernels per step.  Both counts kernels on the tensor cores: softmax, forward, tail (slice sums + loss + dloss/dS +
+        # G image), VJP, softmax VJP = 5 on one GPU; with an exchange the forward's finish kernel runs before it (NCCL: 6 of
+        # ours + NCCL's own; peer memory: finish, exchange+loss, G image = 7).  Trie walk: softmax, counts, finish, loss,
+        # prepare_g, VJP, softmax VJP = 7.
+        tc_both = E.uses_tensor_fwd(table) and E.uses_tensor_vjp(table)
+        launches_per_step = 7 if not tc_both or group is not None else (5 if world == 1 else 6)
         out = {
             "metric": "EODM fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -501,7 +505,8 @@ def main():
             "notes": {"l2": "flushed between timed steps (256 MiB write)",
                       "exchange": None if world == 1 else
                       ("one kernel over NVLink peer memory, fused with the loss" if group is not None else "ncclAllReduce"),
-                      "path": ("forward: %s; VJP: tcgen05 cta_group::2 3xTF32, windows on the M axis, TMA-staged posterior tile"
+                      "path": ("forward: %s; slice sums, loss, dloss/dS and the VJP's G image: one launch; VJP: tcgen05 cta_group::2 "
+                               "3xTF32, windows on the M axis, TMA-staged posterior tile"
                                % ("tcgen05 3xTF32, pairs on the M axis, operand formed in registers and written to TMEM"
                                   if E.uses_tensor_fwd(table) else "cuda-core trie walk (shared-memory operand tile)")
                                if E.uses_tensor_vjp(table) else

@@ -34,7 +34,7 @@ torch.cuda.synchronize()
 fn(C.c_void_p(0))
 lib.eodm_debug_set_path(0)
 names = ["mma_wait_full", "mma_wait_d_empty", "mma_wait_a_full", "mma_total", "epi_wait_d_full", "epi_wait_a_ready", "epi_work",
-         "epi_total", "tma_wait_empty", "tma_total", "stg_wait_free", "stg_total"]
+         "epi_total", "tma_wait_empty", "tma_total", "stg_wait_free", "stg_total", "epi_write", "epi_adds", "epi_prep"]
 v = buf[:148 * 16].view(148, 16).cpu().double()
 tr = buf[148 * 16:].view(5, 256).cpu()
 print("kernel+image ms %.4f" % a.elapsed_time(b))

@@ -79,7 +79,7 @@ struct BArgs {
 
 // cycle counters of the profile buffer (per CTA, 16 slots)
 enum { kProfMmaFull = 0, kProfMmaDEmpty, kProfMmaAFull, kProfMmaTotal, kProfEpiDFull, kProfEpiAReady, kProfEpiWork, kProfEpiTotal,
-       kProfTmaEmpty, kProfTmaTotal, kProfStgFree, kProfStgTotal };
+       kProfTmaEmpty, kProfTmaTotal, kProfStgFree, kProfStgTotal, kProfEpiWrite, kProfEpiAdds, kProfEpiPrep };
 // debug trace of CTA 0: clock64 at five events of every block (first 256 blocks), after the per-CTA counters
 constexpr int kTraceBase = 148 * 16, kTraceLen = 256;
 template <bool ON>
@@ -406,6 +406,7 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
       const float* e_tile = ehi_p + (size_t)buf * (C::kPlane / 4);
       const float* e_row0 = e_tile + w * 4;
       const float* e_row1 = e_tile + (w + 1) * 4;
+      tw.start();
 #pragma unroll
       for (int k = 0; k < VP; ++k) dp_row[k] = 0.f;      // dP_0 partial sums are ADDED to this row
       {
@@ -417,6 +418,7 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         }
 #pragma unroll
         for (int k = 0; k < VP; ++k) dP1[k] = 0.f;
+        tw.stop(kProfEpiPrep);
 #pragma unroll 1
         for (int j = 0; j < C::NB; ++j, ++blk) {
           const int bank = blk & 1;
@@ -436,11 +438,13 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
           if (lane == 0) mbar_arrive_cluster_light(&bars.d_empty[bank], 0);
           if (tid == 128) trace<PROF>(a.prof, 4, (uint32_t)blk);
         }
+        tw.start();
         set_bar();   // every dP_0 row of this set's tile is in before any dP_1 is added to it
         if (w + 1 < 128) {
 #pragma unroll
           for (int k = 0; k < VP; ++k) dp_row[C::LDP + k] += valid ? dP1[k] : 0.f;
         }
+        tw.stop(kProfEpiAdds);
       }
       {
         float dP2[VP];
@@ -465,15 +469,18 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
           if (lane == 0) mbar_arrive_cluster_light(&bars.d_empty[bank], 0);
           if (tid == 128) trace<PROF>(a.prof, 4, (uint32_t)blk);
         }
+        tw.start();
         set_bar();   // dP_1 rows are in
         if (w + 2 < 128) {
 #pragma unroll
           for (int k = 0; k < VP; ++k) dp_row[2 * C::LDP + k] += valid ? dP2[k] : 0.f;
         }
+        tw.stop(kProfEpiAdds);
       }
       // the posterior tile is no longer needed by this warp
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a_free[buf]);
+      tw.start();
       asm volatile("bar.sync 3, 256;" ::: "memory");   // both sets' tiles are complete
       // rows 2..127 are complete: one coalesced write of the sum of the two sets' tiles (index arithmetic on compile-time
       // VP, eight independent elements in flight per thread)
@@ -490,6 +497,7 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
         }
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");   // the tiles are free for the next dP_0 rows
+      tw.stop(kProfEpiWrite);
     }
     tot.stop(kProfEpiTotal);
   }
@@ -672,11 +680,20 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant
   __threadfence();
   // eodm_loss_kernel's order: virtual thread t = 0..1023 adds term[t], term[t + 1024], ...; warps of 32 consecutive t are
   // reduced by the xor tree, then the 32 warp sums by the same tree
-  const volatile float* term = a.term;
-#pragma unroll
+  // (the terms were written by other blocks: L2 loads, issued in batches of 16 so that their latencies overlap -- one
+  // dependent load per addition made this block the longest part of the kernel)
+#pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     float acc = 0.f;
-    for (int z = threadIdx.x + 256 * q; z < a.K; z += 1024) acc += term[z];
+#pragma unroll 1
+    for (int z0 = threadIdx.x + 256 * q; z0 < a.K; z0 += 16 * 1024) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (z0 + u * 1024 < a.K) ? __ldcg(a.term + z0 + u * 1024) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (z0 + u * 1024 < a.K) acc += v[u];
+    }
     acc = warp_sum_t(acc);
     if ((threadIdx.x & 31) == 0) red[8 * q + (threadIdx.x >> 5)] = acc;
   }
