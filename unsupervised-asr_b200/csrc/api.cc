@@ -429,13 +429,16 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   float* N = s->counts + t->K;
   int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
   bool image_ready = false;
-  if (rc == EODM_OK && dlogits && !comm && !s->peer && fwd_path(t) == 3 && use_tensor_bwd(t)) {
-    // both counts kernels on the tensor cores and nothing to exchange: what lies between them -- the forward's slice sums,
-    // the loss, dloss/dS, the VJP's G image -- is one launch
+  const EodmPeerView* pv = s->peer ? eodm_peer_view(s->peer) : nullptr;
+  if (rc == EODM_OK && dlogits && (s->peer ? pv != nullptr : !comm) && fwd_path(t) == 3 && use_tensor_bwd(t)) {
+    // both counts kernels on the tensor cores: what lies between them -- the forward's slice sums, the exchange over peer
+    // memory when the session has a peer group, the loss, dloss/dS, the VJP's G image -- is one launch
     EodmTcfParts parts;
     rc = check_batch(t, s->px, mask, B, T);
     if (rc == EODM_OK) rc = eodm_tcf_launch_main(t, s->px, mask, B, T, session_tcf_ws(s), st, &parts);
-    if (rc == EODM_OK) rc = eodm_tc_tail_launch(t, &parts, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st);
+    if (rc == EODM_OK)
+      rc = pv ? eodm_tc_tail_peer_launch(t, &parts, pv, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st)
+              : eodm_tc_tail_launch(t, &parts, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st);
     image_ready = true;
   } else {
     if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);

@@ -48,6 +48,25 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
 int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S_io, float* N_io, const float* py, float eps,
                         float* loss, float* gS, void* ws_tcb, cudaStream_t st);
 
+// peer.cu -- what a kernel needs to reach the peers' buffers (NVLink peer memory, CUDA IPC); header layout of a buffer:
+// [0] flag u32, [64] step counter u32, [128] error i32, [192], [196] tickets of the multi-CTA tail; then two slots of
+// slot_bytes (K + 1 floats each, alternating by step parity) and a private scratch plane
+#define EODM_MAX_PEERS 8
+#define EODM_PEER_HDR_BYTES 256
+struct EodmPeerView {
+  char* base[EODM_MAX_PEERS];
+  int world, rank, K;
+  unsigned long long slot_bytes;
+  long long timeout_clk;   // give up waiting for a peer after this many SM clocks; <= 0: wait for ever
+};
+struct eodm_peer;
+const EodmPeerView* eodm_peer_view(const eodm_peer* p);   // nullptr until eodm_peer_attach has run (world > 1)
+// the fused tail with the exchange inside: every rank publishes its slice sums, the ranks' counts are added in rank order
+// out of peer memory, then loss, dloss/dS and the G image as in eodm_tc_tail_launch -- one launch
+int eodm_tc_tail_peer_launch(const eodm_table* t, const EodmTcfParts* parts, const EodmPeerView* pv, float* S_out,
+                             float* N_out, const float* py, float eps, float* loss, float* gS, void* ws_tcb,
+                             cudaStream_t st);
+
 // ops.cu -- loss, softmax, materialising op
 int eodm_loss_launch(const float* S, const float* N, const float* py, int K, float eps, float* loss, float* gS,
                      cudaStream_t st);

@@ -24,16 +24,10 @@
 #include "table.h"
 
 namespace {
-constexpr int kMaxPeers = 8;      // the GPUs of one NVSwitch node
+constexpr int kMaxPeers = EODM_MAX_PEERS;      // the GPUs of one NVSwitch node
 constexpr int kThreadsP = 512, kUnrollZ = 8;
-constexpr size_t kHdrBytes = 256;   // [0]: flag (u32), [64]: step counter (u32), [128]: error (i32)
-
-struct PeerView {
-  char* base[kMaxPeers];
-  int world, rank, K;
-  unsigned long long slot_bytes;
-  long long timeout_clk;   // give up waiting for a peer after this many SM clocks; <= 0: wait for ever
-};
+constexpr size_t kHdrBytes = EODM_PEER_HDR_BYTES;   // [0]: flag (u32), [64]: step counter (u32), [128]: error (i32)
+using PeerView = EodmPeerView;
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
@@ -162,6 +156,10 @@ struct eodm_peer {
       return code;                    \
     }                                 \
   } while (0)
+
+const EodmPeerView* eodm_peer_view(const eodm_peer* p) {
+  return (p && (p->attached || p->pv.world == 1)) ? &p->pv : nullptr;
+}
 
 extern "C" int eodm_peer_create(int world, int rank, int K, eodm_peer** out, char handle_out[64]) {
   PEER_REQUIRE(out && handle_out, EODM_EINVAL, "null pointer");

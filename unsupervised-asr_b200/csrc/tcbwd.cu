@@ -629,6 +629,55 @@ __device__ __forceinline__ float warp_sum_t(float v) {
   return v;
 }
 
+// everything a table entry's count s feeds: the loss terms, dloss/dS and the image word of image element i
+__device__ __forceinline__ void tail_element(const TailArgs& a, long long i, int z, float s, float n, bool write_S) {
+  float g = 0.f;
+  for (; z >= 0; z = a.next_dup[z]) {   // duplicates of a trigram share its count; their gradients add up in table order
+    if (write_S) a.S[z] = s;
+    else s = a.S[z];
+    const float pz = s / n, p = a.py[z];
+    a.term[z] = -p * logf(pz + a.eps);
+    const float gz = -p / (pz + a.eps) / n;
+    a.gS[z] = gz;
+    g += gz;
+  }
+  const long long kstep = i >> 10, in = i & 1023;
+  a.img[kstep * 2048 + in] = g;
+  a.img[kstep * 2048 + 1024 + in] = tf32_lo(g);
+}
+// this trigram's count from the forward's slice partials, added in slice order (as eodm_tc_fwd3_finish_kernel does)
+__device__ __forceinline__ float tail_slice_sum(const TailArgs& a, int z) {
+  const float* p = a.partS + ((size_t)a.ids[3 * z] * a.vp + a.ids[3 * z + 1]) * a.vp + a.ids[3 * z + 2];
+  float s = 0.f;
+  for (int sl = 0; sl < a.n_slices; ++sl) s += p[(size_t)sl * a.slice_stride];
+  return s;
+}
+// the K loss terms in eodm_loss_kernel's order: virtual thread t = 0..1023 adds term[t], term[t + 1024], ...; warps of 32
+// consecutive t are reduced by the xor tree, then the 32 warp sums by the same tree.  (The terms were written by other
+// blocks: L2 loads, issued in batches of 16 so that their latencies overlap.)  Called by all 256 threads of one block.
+__device__ __forceinline__ void tail_loss_reduce(const TailArgs& a, float* red) {
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    float acc = 0.f;
+#pragma unroll 1
+    for (int z0 = threadIdx.x + 256 * q; z0 < a.K; z0 += 16 * 1024) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (z0 + u * 1024 < a.K) ? __ldcg(a.term + z0 + u * 1024) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (z0 + u * 1024 < a.K) acc += v[u];
+    }
+    acc = warp_sum_t(acc);
+    if ((threadIdx.x & 31) == 0) red[8 * q + (threadIdx.x >> 5)] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const float v = warp_sum_t(red[threadIdx.x]);
+    if (threadIdx.x == 0) a.loss[0] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant__ TailArgs a) {
   __shared__ float n_s;
   __shared__ unsigned last;
@@ -649,28 +698,8 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant
   const float n = n_s;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.zmap_len) {
-    float g = 0.f;
-    int z = a.zmap[i];
-    if (z >= 0) {
-      float s;
-      if (a.partS) {
-        const float* p = a.partS + ((size_t)a.ids[3 * z] * a.vp + a.ids[3 * z + 1]) * a.vp + a.ids[3 * z + 2];
-        s = 0.f;
-        for (int sl = 0; sl < a.n_slices; ++sl) s += p[(size_t)sl * a.slice_stride];
-      }
-      for (; z >= 0; z = a.next_dup[z]) {   // duplicates of a trigram share its count; their gradients add up in table order
-        if (a.partS) a.S[z] = s;
-        else s = a.S[z];
-        const float pz = s / n, p = a.py[z];
-        a.term[z] = -p * logf(pz + a.eps);
-        const float gz = -p / (pz + a.eps) / n;
-        a.gS[z] = gz;
-        g += gz;
-      }
-    }
-    const long long kstep = i >> 10, in = i & 1023;
-    a.img[kstep * 2048 + in] = g;
-    a.img[kstep * 2048 + 1024 + in] = tf32_lo(g);
+    const int z = a.zmap[i];
+    tail_element(a, i, z, (z >= 0 && a.partS) ? tail_slice_sum(a, z) : 0.f, n, a.partS != nullptr);
   }
   __threadfence();
   __syncthreads();
@@ -678,32 +707,107 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // eodm_loss_kernel's order: virtual thread t = 0..1023 adds term[t], term[t + 1024], ...; warps of 32 consecutive t are
-  // reduced by the xor tree, then the 32 warp sums by the same tree
-  // (the terms were written by other blocks: L2 loads, issued in batches of 16 so that their latencies overlap -- one
-  // dependent load per addition made this block the longest part of the kernel)
-#pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
-    float acc = 0.f;
-#pragma unroll 1
-    for (int z0 = threadIdx.x + 256 * q; z0 < a.K; z0 += 16 * 1024) {
-      float v[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = (z0 + u * 1024 < a.K) ? __ldcg(a.term + z0 + u * 1024) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (z0 + u * 1024 < a.K) acc += v[u];
+  tail_loss_reduce(a, red);
+  if (threadIdx.x == 0) *a.done = 0;   // ready for the next step (graph replays included)
+}
+
+// ---- the same with the exchange of a batch-sharded step inside (one process per GPU, buffers shared through CUDA IPC:
+//      peer.cu).  Phase A: every thread writes its trigrams' slice sums (this rank's partial counts) into the rank's
+//      peer-visible slot; the block that takes the last ticket raises the rank's flag to the step number.  Every block then
+//      waits for all ranks' flags (acquire loads over NVLink; the grid is sized to be co-resident, so a waiting block
+//      never keeps an unpublished one off the SMs).  Phase B: the ranks' counts are read straight out of peer memory and
+//      added in rank order -- identical bits on every rank -- and feed the loss terms, dloss/dS and the G image exactly as
+//      above.  Slots alternate by step parity (peer.cu explains why that is enough); the step counter is advanced by the
+//      last block, so a captured graph replays.  A peer that never arrives: NaN everywhere, error flag set.
+__device__ __forceinline__ unsigned tail_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_constant__ TailArgs a,
+                                                                const __grid_constant__ EodmPeerView pv) {
+  __shared__ float n_s;
+  __shared__ unsigned last;
+  __shared__ int bad_s;
+  __shared__ float red[32];
+  char* mine = pv.base[pv.rank];
+  unsigned* ctr = reinterpret_cast<unsigned*>(mine + 64);
+  unsigned* ticket_a = reinterpret_cast<unsigned*>(mine + 192);
+  unsigned* ticket_b = reinterpret_cast<unsigned*>(mine + 196);
+  const unsigned step = *reinterpret_cast<volatile unsigned*>(ctr) + 1u;   // advanced by the last block of this launch
+  const size_t slot_off = EODM_PEER_HDR_BYTES + (size_t)(step & 1u) * pv.slot_bytes;
+  float* slot = reinterpret_cast<float*>(mine + slot_off);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // ---- phase A
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zmap_len; i += stride) {
+    int z = a.zmap[i];
+    if (z >= 0) {
+      const float s = tail_slice_sum(a, z);
+      for (; z >= 0; z = a.next_dup[z]) slot[z] = s;   // (every trigram sits in both GEMMs' images: written twice, same value)
     }
-    acc = warp_sum_t(acc);
-    if ((threadIdx.x & 31) == 0) red[8 * q + (threadIdx.x >> 5)] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int c = 0;
+    for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
+    slot[pv.K] = (float)c;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bad_s = 0;
+    if (atomicAdd(ticket_a, 1u) == gridDim.x - 1u) {   // every block of this rank has published
+      *ticket_a = 0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned*>(mine)), "r"(step) : "memory");
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const float v = warp_sum_t(red[threadIdx.x]);
-    if (threadIdx.x == 0) {
-      a.loss[0] = v;
-      *a.done = 0;   // ready for the next step (graph replays included)
+  if (threadIdx.x < pv.world) {
+    const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
+    const long long t0 = clock64();
+    while ((int)(tail_ld_acquire_sys(flag) - step) < 0) {   // signed difference: the counter may wrap
+      if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {
+        bad_s = 1;
+        break;
+      }
     }
+  }
+  __syncthreads();
+  const bool bad = bad_s != 0;
+  // ---- phase B
+  if (threadIdx.x == 0) {
+    float n = 0.f;
+    for (int r = 0; r < pv.world; ++r) n += __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + pv.K);
+    if (bad) n = __int_as_float(0x7fc00000);
+    n_s = n;
+    if (blockIdx.x == 0) a.N[0] = n;
+  }
+  __syncthreads();
+  const float n = n_s;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zmap_len; i += stride) {
+    const int z = a.zmap[i];
+    float s = 0.f;
+    if (z >= 0) {
+      float v[EODM_MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < EODM_MAX_PEERS; ++r)
+        v[r] = r < pv.world ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
+#pragma unroll
+      for (int r = 0; r < EODM_MAX_PEERS; ++r) s += v[r];   // rank order; absent ranks add +0
+    }
+    tail_element(a, i, z, s, n, true);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket_b, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  tail_loss_reduce(a, red);
+  if (threadIdx.x == 0) {
+    *ticket_b = 0;
+    *ctr = step;
+    if (bad_s) *reinterpret_cast<int*>(mine + 128) = 1;
   }
 }
 
@@ -775,6 +879,46 @@ int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_tc_tail_kernel launch failed: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  return EODM_OK;
+}
+
+int eodm_tc_tail_peer_launch(const eodm_table* t, const EodmTcfParts* parts, const EodmPeerView* pv, float* S_out,
+                             float* N_out, const float* py, float eps, float* loss, float* gS, void* ws_tcb,
+                             cudaStream_t st) {
+  if (!eodm_tcb_supported(t) || !t->d_ids || !parts || !pv || pv->K != t->K) {
+    eodm_set_error("fused tail with exchange: needs a trigram-only table over V <= 48, the forward's slice sums and a peer "
+                   "group bootstrapped for this table's K");
+    return EODM_EUNSUPPORTED;
+  }
+  TailArgs a;
+  a.partS = parts->partS;
+  a.partN = parts->partN;
+  a.n_slices = parts->n_slices;
+  a.vp = parts->vp;
+  a.slice_stride = parts->slice_stride;
+  a.S = S_out;
+  a.N = N_out;
+  a.py = py;
+  a.ids = t->d_ids;
+  a.zmap = t->tcb.d_zmap;
+  a.next_dup = t->tcb.d_next;
+  a.zmap_len = t->tcb.zmap_len;
+  a.K = t->K;
+  a.eps = eps;
+  a.gS = gS;
+  a.img = (float*)(((uintptr_t)ws_tcb + 1023) & ~(uintptr_t)1023);
+  a.term = a.img + (size_t)t->tcb.zmap_len * 2;
+  a.done = nullptr;   // the tickets live in the peer buffer's header
+  a.loss = loss;
+  // co-resident grid: three blocks of 256 threads per SM at most (every block spins on the peers' flags in the middle)
+  long long grid = (a.zmap_len + 255) / 256;
+  if (grid > 3LL * t->sm_count) grid = 3LL * t->sm_count;
+  eodm_tc_tail_peer_kernel<<<(unsigned)grid, 256, 0, st>>>(a, *pv);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    eodm_set_error("eodm_tc_tail_peer_kernel launch failed: %s", cudaGetErrorString(e));
     return EODM_ECUDA;
   }
   return EODM_OK;
