@@ -762,40 +762,76 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_con
     }
   }
   __syncthreads();
-  if (threadIdx.x < pv.world) {
-    const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
-    const long long t0 = clock64();
-    while ((int)(tail_ld_acquire_sys(flag) - step) < 0) {   // signed difference: the counter may wrap
-      if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {
-        bad_s = 1;
-        break;
+  // Block 0 alone watches the peers' flags over NVLink and then raises a LOCAL go word the other blocks watch in their own
+  // L2: with every block polling remote memory (3 000 pollers per rank) the polls queued up on the links and a raised flag
+  // was seen tens of microseconds late (0.433 ms per step at 8 GPUs against 0.401 with NCCL, profiles/r02_scaling.md).
+  unsigned* go = reinterpret_cast<unsigned*>(mine + 200);   // step number once every rank has published; [204]: timed out
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < pv.world) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
+      const long long t0 = clock64();
+      while ((int)(tail_ld_acquire_sys(flag) - step) < 0) {   // signed difference: the counter may wrap
+        if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {
+          bad_s = 1;
+          break;
+        }
       }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *reinterpret_cast<volatile int*>(mine + 204) = bad_s;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(step) : "memory");
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
+      } while (v != step);
+      bad_s = *reinterpret_cast<volatile int*>(mine + 204);
     }
   }
   __syncthreads();
   const bool bad = bad_s != 0;
-  // ---- phase B
-  if (threadIdx.x == 0) {
-    float n = 0.f;
-    for (int r = 0; r < pv.world; ++r) n += __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + pv.K);
-    if (bad) n = __int_as_float(0x7fc00000);
+  // ---- phase B1: the ranks' counts, added in rank order, into a local plane -- consecutive threads read consecutive
+  //      entries, so a rank serves 128-byte requests (a 40 KB slot per reader).  Reading the peers entry by entry from
+  //      phase B2's image order instead (scattered 4-byte loads, 155 k sectors served per rank) cost ~25 us at 8 GPUs.
+  float* sum = reinterpret_cast<float*>(mine + EODM_PEER_HDR_BYTES + 2 * pv.slot_bytes);
+  for (long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x; z <= pv.K; z += stride) {
+    float v[EODM_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < EODM_MAX_PEERS; ++r)
+      v[r] = r < pv.world ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < EODM_MAX_PEERS; ++r) t += v[r];   // rank order; absent ranks add +0
+    sum[z] = bad ? __int_as_float(0x7fc00000) : t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {   // grid barrier: the plane is complete before anyone reads it
+    unsigned* ticket_c = reinterpret_cast<unsigned*>(mine + 208);
+    unsigned* go2 = reinterpret_cast<unsigned*>(mine + 212);
+    if (atomicAdd(ticket_c, 1u) == gridDim.x - 1u) {
+      *ticket_c = 0;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go2), "r"(step) : "memory");
+    }
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go2) : "memory");
+    } while (v != step);
+    const float n = __ldcg(sum + pv.K);
     n_s = n;
     if (blockIdx.x == 0) a.N[0] = n;
   }
   __syncthreads();
+  // ---- phase B2: loss terms, dloss/dS, G image
   const float n = n_s;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zmap_len; i += stride) {
     const int z = a.zmap[i];
-    float s = 0.f;
-    if (z >= 0) {
-      float v[EODM_MAX_PEERS];
-#pragma unroll
-      for (int r = 0; r < EODM_MAX_PEERS; ++r)
-        v[r] = r < pv.world ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
-#pragma unroll
-      for (int r = 0; r < EODM_MAX_PEERS; ++r) s += v[r];   // rank order; absent ranks add +0
-    }
-    tail_element(a, i, z, s, n, true);
+    tail_element(a, i, z, z >= 0 ? __ldcg(sum + z) : 0.f, n, true);
   }
   __threadfence();
   __syncthreads();
