@@ -139,26 +139,6 @@ def test_every_tile_variant(eodm, case):
         lib.eodm_debug_set_tiling(0, 0)
 
 
-@pytest.mark.parametrize("seed,V,n,K,B,T", [(1, 16, 2, 100, 3, 40), (2, 48, 3, 3000, 5, 150), (3, 40, 5, 1000, 6, 70),
-                                             (4, 48, 3, 10000, 40, 300), (5, 64, 4, 2500, 4, 90)])
-def test_tensor_core_counts_vs_oracle(eodm, seed, V, n, K, B, T):
-    """The tcgen05 forward path (3xTF32, accumulators drained every 16 MMA steps), pinned through the debug hook."""
-    from eodm_b200._lib import lib
-    ids, py = eodm.synth.table(V, n, K, seed=seed)
-    logits, mask = O.synth_batch(B, T, V, seed=seed, len_lo=n)
-    dev = _dev()
-    table = eodm.NgramTable.from_ids(ids, V, device=0)
-    px = torch.tensor(O.softmax(logits).astype(np.float32), device=dev)
-    S_ref, N_ref = O.counts_fwd(px.cpu().numpy().astype(np.float64), mask, ids, n)
-    try:
-        lib.eodm_debug_set_path(2)
-        counts = eodm.counts_fwd(table, px, torch.tensor(mask, device=dev)).cpu().numpy()
-    finally:
-        lib.eodm_debug_set_path(0)
-    assert counts[K] == N_ref
-    assert (np.abs(counts[:K] - S_ref) / S_ref).max() <= TOL
-
-
 @pytest.mark.parametrize("seed,V,K,B,T,len_lo,dup", [
     (1, 48, 10000, 6, 100, None, False),     # BASELINE configs[1] table
     (2, 48, 3000, 40, 300, 3, True),         # ragged, duplicates, several tiles per slice

@@ -66,11 +66,10 @@ static int check_batch(const eodm_table* t, const void* px, const void* mask, in
 static int g_path = 0;
 extern "C" void eodm_debug_set_path(int path) { g_path = path; }
 
-// forward: 0 = trie walk, 2 = tensor.cu (any full-order table), 3 = tcfwd.cu (trigram-only tables over V <= 48)
+// forward: 0 = trie walk, 3 = tcfwd.cu (trigram-only tables over V <= 48)
 static int fwd_path(const eodm_table* t) {
   if (g_path == 1) return 0;
-  if (g_path == 4) return eodm_tc_supported(t) ? 2 : 0;
-  if (g_path == 2) return eodm_tcf_supported(t) ? 3 : (eodm_tc_supported(t) ? 2 : 0);
+  if (g_path == 2) return eodm_tcf_supported(t) ? 3 : 0;
   if (!eodm_tcf_supported(t)) return 0;
   // measured at timit_c2 (profiles/r02_tcfwd.md): the tensor-core forward costs ~500 SM-clocks per row whatever the table
   // holds (it is bound by forming the 2304 x W operand, not by the MMAs); the walk costs ~0.057 per trie node and row.
@@ -79,7 +78,6 @@ static int fwd_path(const eodm_table* t) {
 }
 
 static size_t counts_ws_aligned(const eodm_table* t) { return (eodm_counts_workspace_bytes(t) + 255) & ~(size_t)255; }
-static size_t tc_ws_aligned(const eodm_table* t) { return (eodm_tc_workspace_bytes(t) + 255) & ~(size_t)255; }
 static size_t tcb_ws_aligned(const eodm_table* t) { return (eodm_tcb_workspace_bytes(t) + 255) & ~(size_t)255; }
 
 // The tensor-core VJP (tcbwd.cu) costs 2 * ceil(VP^2/256) * (VP/8) * 3 MMAs of 128 clk per 126 rows whatever the table
@@ -99,7 +97,7 @@ extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
   (void)B;
   (void)T;
   if (!t || t->device < 0) return 0;
-  return counts_ws_aligned(t) + tc_ws_aligned(t) + tcb_ws_aligned(t) + eodm_tcf_workspace_bytes(t);
+  return counts_ws_aligned(t) + tcb_ws_aligned(t) + eodm_tcf_workspace_bytes(t);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -109,10 +107,8 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
   const int path = fwd_path(t);
   if (path == 3)
-    return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tc_ws_aligned(t) + tcb_ws_aligned(t),
+    return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tcb_ws_aligned(t),
                            (cudaStream_t)stream);
-  if (path == 2)
-    return eodm_tc_fwd_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t), (cudaStream_t)stream);
   return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream);
 }
 
@@ -132,7 +128,7 @@ static int counts_bwd_any(const eodm_table* t, const float* px, const uint8_t* m
   if (rc != EODM_OK) return rc;
   REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
   if (use_tensor_bwd(t))
-    return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t) + tc_ws_aligned(t),
+    return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t),
                            (cudaStream_t)stream, accumulate);
   return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate);
 }
@@ -388,7 +384,7 @@ extern "C" int eodm_session_set_peer(eodm_session* s, eodm_peer* peer) {
 }
 
 // exchange (if any) + loss + dloss/dS from this rank's packed counts
-static void* session_tcb_ws(const eodm_session* s) { return (char*)s->ws + counts_ws_aligned(s->t) + tc_ws_aligned(s->t); }
+static void* session_tcb_ws(const eodm_session* s) { return (char*)s->ws + counts_ws_aligned(s->t); }
 static void* session_tcf_ws(const eodm_session* s) { return (char*)session_tcb_ws(s) + tcb_ws_aligned(s->t); }
 
 // *image_ready: the tensor-core VJP's G image was written along with the loss (eodm_tc_tail_launch) -- the VJP launches of

@@ -15,13 +15,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
                            float* dpx, void* ws, cudaStream_t st, int accumulate = 0);   // accumulate: dpx += ...
 
-// tensor.cu -- tcgen05 path for full-order tables
-bool eodm_tc_supported(const eodm_table* t);
-size_t eodm_tc_workspace_bytes(const eodm_table* t);
-int eodm_tc_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                       void* ws, cudaStream_t st);
-
-// tcfwd.cu -- tcgen05 forward for trigram-only tables over V <= 48 (second generation of tensor.cu)
+// tcfwd.cu -- tcgen05 forward for trigram-only tables over V <= 48
 bool eodm_tcf_supported(const eodm_table* t);
 size_t eodm_tcf_workspace_bytes(const eodm_table* t);
 int eodm_tcf_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N, void* ws,

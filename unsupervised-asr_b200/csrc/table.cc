@@ -438,37 +438,6 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
       if ((rc = upload(t, zmap, &t->tcb.d_zmap)) == EODM_OK) rc = upload(t, next, &t->tcb.d_next);
     }
   }
-  for (int j = 0; j < EODM_MAX_N; ++j) t->rows[j] = EodmRows{0, nullptr, nullptr, nullptr};
-  if (rc == EODM_OK && !host_only && t->full_order) {
-    for (int j = 0; j < n && rc == EODM_OK; ++j) {
-      // sort n-grams by the tuple of their other positions; equal tuples share a row
-      std::vector<int32_t> idx(K), zrow(K), zcol(K), tok;
-      std::iota(idx.begin(), idx.end(), 0);
-      auto key_less = [&](int32_t a, int32_t b) {
-        for (int p = 0; p < n; ++p) {
-          if (p == j) continue;
-          int32_t x = ids[(size_t)a * n + p], y = ids[(size_t)b * n + p];
-          if (x != y) return x < y;
-        }
-        return false;
-      };
-      std::stable_sort(idx.begin(), idx.end(), key_less);
-      int n_rows = 0;
-      for (int i = 0; i < K; ++i) {
-        if (i == 0 || key_less(idx[i - 1], idx[i])) {
-          for (int p = 0; p < n; ++p)
-            if (p != j) tok.push_back(ids[(size_t)idx[i] * n + p]);
-          ++n_rows;
-        }
-        zrow[idx[i]] = n_rows - 1;
-        zcol[idx[i]] = ids[(size_t)idx[i] * n + j];
-      }
-      t->rows[j].n_rows = n_rows;
-      if ((rc = upload(t, tok, &t->rows[j].d_tok)) != EODM_OK) break;
-      if ((rc = upload(t, zrow, &t->rows[j].d_zrow)) != EODM_OK) break;
-      if ((rc = upload(t, zcol, &t->rows[j].d_zcol)) != EODM_OK) break;
-    }
-  }
   if (rc == EODM_OK && !host_only) {
     std::vector<int32_t> off(V + 1, 0), zj;
     for (int z = 0; z < K; ++z)

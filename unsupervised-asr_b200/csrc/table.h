@@ -70,16 +70,6 @@ struct EodmTrieHost {  // host mirror (tests, eodm_table_debug_trie)
   std::vector<int32_t> perm;
 };
 
-// Tensor-core path (tensor.cu): for window position j, the distinct tuples of the tokens at the OTHER
-// positions (ascending position order) are the rows of a dense [rows x V] matrix; n-gram z sits at
-// (zrow[z], ids[z][j]).  Built only when every n-gram has order == n >= 2.
-struct EodmRows {
-  int n_rows;
-  const int32_t* d_tok;   // [n_rows][n-1]
-  const int32_t* d_zrow;  // [K]
-  const int32_t* d_zcol;  // [K]
-};
-
 // Tensor-core VJP (tcbwd.cu): trigram-only tables over V <= 64.  zmap lists, in the order the kernel's stages consume
 // the dense G[a,b,c] image, the first table entry that is the trigram of each image element (-1: none); next chains
 // the duplicates of an entry in table order.
@@ -114,7 +104,6 @@ struct eodm_table {
   int32_t* d_next_dup;        // [K] next n-gram with the same ids (-1: none): chains of duplicates, for the
   int32_t* d_is_first;        //     dense-bigram scatter; d_is_first[z] = 1 if z heads its chain
   bool full_order;            // every n-gram has order == n
-  EodmRows rows[EODM_MAX_N];
   EodmTcb tcb;
   int64_t node_offset[EODM_MAX_N];
   int64_t total_nodes_padded;

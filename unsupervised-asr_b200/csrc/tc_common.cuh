@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / mbarrier helpers shared by tensor.cu and bigram.cu (sm_100a inline PTX).
+// tcgen05 / TMEM / mbarrier helpers shared by tcfwd.cu, tcbwd.cu and bigram.cu (sm_100a inline PTX).
 #ifndef EODM_TC_COMMON_CUH_
 #define EODM_TC_COMMON_CUH_
 #include <cuda_runtime.h>

@@ -1,4 +1,4 @@
-// Expected trigram counts on the 5th-generation tensor cores (tcgen05 + TMEM), second generation of tensor.cu.
+// Expected trigram counts on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
 //   S[(a,b), c] = sum_w valid(w) Q[(a,b), w] Pm[c, w],   Q[(a,b), w] = (px[w,a] + eps)(px[w+1,b] + eps),
 //                                                        Pm[c, w]   = valid(w) (px[w+2,c] + eps)
@@ -9,7 +9,7 @@
 // one shared-memory operand per (trie node, window) and runs at 72 % of the shared-memory wavefront rate; here the operand
 // reuse happens inside the tensor core.
 //
-// What changed against tensor.cu (540 us at timit_c2, kept as the general-n path), all of it measured:
+// What changed against round 1's tensor-core forward (tensor.cu, 540 us at timit_c2, since removed), all of it measured:
 //   * tcgen05.mma costs ~45 clk for ANY N <= 96 at M = 128 (tools/ubench_mma2.cu), so the B operand is [Pm_hi; Pm_lo] stacked
 //     along N (N = 96): one MMA yields Q_hi Pm_hi and Q_hi Pm_lo side by side, a second (N = 48) adds Q_lo Pm_hi -- two MMAs
 //     per K-step for the 3xTF32 product instead of three, the two halves of a row are added when the accumulator is read;
@@ -29,10 +29,10 @@
 // out of the staged tile with no per-stage work.  At the end every CTA writes its sums to a per-slice partial and a
 // second kernel gathers the K table entries and adds the slices in a fixed order: deterministic, no float atomics.
 //
-// Status (profiles/r02_tcfwd.md): 0.237 ms at timit_c2 against 0.252 ms for the trie walk and 0.55 ms for tensor.cu.  The
-// MMAs would take 0.08 ms; the kernel is bound by the eight producer warps (two per scheduler: ~100 instructions per
-// 16 windows and row, issued at one per ~6 clk) -- the generated operand, 2304 x W products split into hi and remainder,
-// is the cost of putting a Khatri-Rao contraction on a GEMM unit.
+// Status (profiles/r02_tcfwd.md): 0.173 ms at timit_c2 against 0.252 ms for the trie walk.  The MMAs would take 0.08 ms;
+// the kernel is bound by the shared-memory data pipe (83 % busy: two words loaded per product formed, the B tile read by
+// the tensor core, the staging stores) -- the generated operand, 2304 x W products split into hi and remainder, is the
+// cost of putting a Khatri-Rao contraction on a GEMM unit.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
