@@ -659,6 +659,66 @@ def test_device_step_is_cuda_graph_capturable(eodm):
     sess.close()
 
 
+def test_fused_tail_and_peer_tail_on_one_gpu(eodm):
+    """The launch between the two tensor-core kernels (eodm_tc_tail_kernel: slice sums, N, loss, dloss/dS, G image) and
+    its variant with the exchange inside (eodm_tc_tail_peer_kernel, here with a peer group of ONE rank so that it runs on
+    a 1-GPU box): same bits as each other, also when replayed from a CUDA graph (the step counter and the tickets live on
+    the device); both, and the walk path's separate kernels, against the oracle."""
+    from eodm_b200._lib import lib
+    from eodm_b200.dist import PeerGroup
+    dev = _dev()
+    V, n, K, B, T = 48, 3, 3000, 6, 150
+    ids, py = eodm.synth.table(V, n, K, seed=31)
+    ids[K - 1] = ids[7]                                      # a duplicated trigram
+    logits, mask = O.synth_batch(B, T, V, seed=31, len_lo=20)
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    lg = torch.tensor(logits, device=dev)
+    m = torch.tensor(mask.astype(np.uint8), device=dev)
+    st = torch.cuda.current_stream()
+
+    def run(sess):
+        loss, dl = torch.zeros(1, device=dev), torch.zeros_like(lg)
+        sess.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss.data_ptr(), dl.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        return loss, dl
+
+    try:
+        lib.eodm_debug_set_path(2)                           # both counts kernels on the tensor cores
+        plain = eodm.Session(table, py, B, T)
+        l_tail, d_tail = run(plain)
+        peer = eodm.Session(table, py, B, T)
+        group = PeerGroup.bootstrap(1, 0, K, lambda mine: [mine])
+        peer.set_peer(group)
+        l_peer, d_peer = run(peer)
+        l_peer2, d_peer2 = run(peer)                         # the other slot
+        loss_g, dl_g = torch.zeros(1, device=dev), torch.zeros_like(lg)
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                peer.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss_g.data_ptr(), dl_g.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            loss_g.zero_(); dl_g.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(loss_g, l_tail) and torch.equal(dl_g, d_tail)
+        assert not group.failed()
+        lib.eodm_debug_set_path(1)                           # trie walk: finish, loss, prepare_g as separate kernels
+        walk = eodm.Session(table, py, B, T)
+        l_walk, d_walk = run(walk)
+    finally:
+        lib.eodm_debug_set_path(0)
+    assert torch.equal(l_tail, l_peer) and torch.equal(d_tail, d_peer)
+    assert torch.equal(l_tail, l_peer2) and torch.equal(d_tail, d_peer2)
+    ref = O.eodm_loss_direct(logits, mask, ids, n, py)
+    for loss, d in ((l_tail, d_tail), (l_walk, d_walk)):
+        assert abs(float(loss) - ref["loss"]) <= TOL * abs(ref["loss"])
+        assert rel_max(d.cpu().numpy(), ref["dlogits"]) <= TOL
+    for s_ in (plain, peer, walk):
+        s_.close()
+
+
 def test_legacy_partial_sums(eodm):
     """SURVEY 8a row a6 -- models/EODM.py:28-52: un-normalised (pz, K) per device, K = the mask cut to the window
     starts; two "devices" (halves of the batch) summed on the host and divided as main_es.py:331-335 does."""
