@@ -93,11 +93,16 @@ static bool use_tensor_bwd(const eodm_table* t) {
   return tc_clk_per_row < walk_clk_per_row;
 }
 
+static size_t tcf_ws_aligned(const eodm_table* t) { return (eodm_tcf_workspace_bytes(t) + 255) & ~(size_t)255; }
+// the row-packing region (counts.cu) sits behind the per-table regions: its offset does not depend on the batch
+static void* pack_ws_of(const eodm_table* t, void* ws) {
+  return (char*)ws + counts_ws_aligned(t) + tcb_ws_aligned(t) + tcf_ws_aligned(t);
+}
+
 extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
-  (void)B;
-  (void)T;
   if (!t || t->device < 0) return 0;
-  return counts_ws_aligned(t) + tcb_ws_aligned(t) + eodm_tcf_workspace_bytes(t);
+  const long long NR = (long long)(B > 0 ? B : 0) * (T > 0 ? T : 0);
+  return counts_ws_aligned(t) + tcb_ws_aligned(t) + tcf_ws_aligned(t) + eodm_pack_workspace_bytes(NR);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -109,7 +114,7 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   if (path == 3)
     return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tcb_ws_aligned(t),
                            (cudaStream_t)stream);
-  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream);
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream, pack_ws_of(t, ws));
 }
 
 // The reference's older multi-device step (models/EODM.py:28-52, main_es.py:135,331-335) returns UN-normalised
@@ -130,7 +135,7 @@ static int counts_bwd_any(const eodm_table* t, const float* px, const uint8_t* m
   if (use_tensor_bwd(t))
     return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t),
                            (cudaStream_t)stream, accumulate);
-  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate);
+  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate, pack_ws_of(t, ws));
 }
 
 extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,

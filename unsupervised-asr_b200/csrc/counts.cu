@@ -64,6 +64,134 @@ struct BwdArgs {
   TrieArg trie[EODM_MAX_N];
 };
 
+// ---- Row packing.  A ragged batch arrives padded to [B][T]; a tile of padded rows costs a full trie walk however few of
+// its rows can start a window (config 3: 37 % of the rows are padding, spread over every tile).  Before a walk, three small
+// kernels list the rows that take part in ANY valid window -- a window start, or one of the n-1 rows after one -- in
+// their original order: rowmap[p] = padded row, wflag[p] = 1 if a window may start at packed row p.  A valid window's
+// rows are consecutive padded rows of one utterance and all of them are listed, so they are consecutive packed rows as
+// well: in the packed index space the batch is ONE sequence with a window-start flag per row, which is what the walk
+// kernels need.  They gather the posterior rows through rowmap when they stage a tile and scatter the gradient rows
+// through it when they write one; the tile height is chosen on the device from the packed row count.
+struct PackView {
+  const int* rowmap;        // [NR] packed row -> padded row (nullptr: no packing)
+  const uint8_t* wflag;     // [NR] a window may start at this packed row
+  const int* counts;        // [0] packed rows, [1] valid frames (N of models/EODM.py:20)
+};
+constexpr int kPackRows = 1024;   // rows per block of the pack kernels (256 threads x 4 consecutive rows)
+
+__device__ __forceinline__ bool pack_wstart(const uint8_t* __restrict__ mask, long long row, int T, int n) {
+  return __ldg(mask + row) != 0 && (int)(row % T) <= T - n;
+}
+// keep[row]: some window start lies in rows t-(n-1) .. t of the row's utterance
+__device__ __forceinline__ bool pack_keep(const uint8_t* __restrict__ mask, long long row, long long NR, int T, int n) {
+  if (row >= NR) return false;
+  const int t = (int)(row % T);
+  for (int d = 0; d < n && d <= t; ++d)
+    if (pack_wstart(mask, row - d, T, n)) return true;
+  return false;
+}
+__global__ void __launch_bounds__(256) eodm_pack_count_kernel(const uint8_t* __restrict__ mask, long long NR, int T, int n,
+                                                              int* __restrict__ bsum, int* __restrict__ bfr) {
+  __shared__ int red[2][8];
+  const long long r0 = (long long)blockIdx.x * kPackRows + threadIdx.x * 4;
+  int k = 0, f = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    k += pack_keep(mask, r0 + u, NR, T, n);
+    f += (r0 + u < NR) && __ldg(mask + r0 + u) != 0;
+  }
+  k = __reduce_add_sync(0xffffffffu, k);
+  f = __reduce_add_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = k;
+    red[1][threadIdx.x >> 5] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    bsum[blockIdx.x] = a;
+    bfr[blockIdx.x] = b;
+  }
+}
+// exclusive scan of the block counts (one block; integer arithmetic: exact), totals into counts[0..1]
+__global__ void __launch_bounds__(1024) eodm_pack_scan_kernel(int* __restrict__ bsum, const int* __restrict__ bfr, int n_blk,
+                                                              int* __restrict__ counts) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s, frames_s;
+  if (threadIdx.x == 0) {
+    carry_s = 0;
+    frames_s = 0;
+  }
+  __syncthreads();
+  for (int base = 0; base < n_blk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blk ? bsum[i] : 0, fr = i < n_blk ? bfr[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    const int ftot = __reduce_add_sync(0xffffffffu, fr);
+    if ((threadIdx.x & 31) == 0 && ftot) atomicAdd(&frames_s, ftot);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      wsum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int before = carry_s + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0) + x - v;
+    if (i < n_blk) bsum[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[0] = carry_s;
+    counts[1] = frames_s;
+  }
+}
+__global__ void __launch_bounds__(256) eodm_pack_fill_kernel(const uint8_t* __restrict__ mask, long long NR, int T, int n,
+                                                             const int* __restrict__ boff, int* __restrict__ rowmap,
+                                                             uint8_t* __restrict__ wflag) {
+  __shared__ int wsum[8];
+  const long long r0 = (long long)blockIdx.x * kPackRows + threadIdx.x * 4;
+  bool keep[4];
+  int k = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    keep[u] = pack_keep(mask, r0 + u, NR, T, n);
+    k += keep[u];
+  }
+  int x = k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+  __syncthreads();
+  int p = boff[blockIdx.x] + x - k;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) p += wsum[w];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (keep[u]) {
+      rowmap[p] = (int)(r0 + u);
+      wflag[p] = pack_wstart(mask, r0 + u, T, n) ? 1 : 0;
+      ++p;
+    }
+}
+
 __host__ __device__ inline int odd_ld(int x) { return x | 1; }
 
 // first unit whose cost prefix reaches `target`
@@ -98,7 +226,7 @@ __device__ __forceinline__ int root_of_unit(const TrieArg& tr, int u) {
 // Stage rows [row0, row0 + nrows) of px, plus eps, transposed into Ps[v][ld]; columns nrows .. ncols-1 and
 // rows outside [0, NR) are staged as zero: their windows are masked, but 0 * garbage must stay 0.
 __device__ __forceinline__ void stage_tile(float* Ps, int ld, const float* __restrict__ px, long long row0, int nrows,
-                                           int ncols, long long NR, int V) {
+                                           int ncols, long long NR, int V, const int* __restrict__ rowmap = nullptr) {
   NR = (row0 + nrows < NR) ? row0 + nrows : NR;
   nrows = ncols;
   if ((V & 3) == 0) {
@@ -109,6 +237,7 @@ __device__ __forceinline__ void stage_tile(float* Ps, int ld, const float* __res
       long long gr = row0 + r;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr >= 0 && gr < NR) {
+        if (rowmap) gr = __ldg(rowmap + gr);
         x = __ldg(reinterpret_cast<const float4*>(px + gr * V) + c4);
         x.x += kEps; x.y += kEps; x.z += kEps; x.w += kEps;
       }
@@ -121,7 +250,7 @@ __device__ __forceinline__ void stage_tile(float* Ps, int ld, const float* __res
       int r = idx / V, v = idx - r * V;
       long long gr = row0 + r;
       float x = 0.f;
-      if (gr >= 0 && gr < NR) x = __ldg(px + gr * V + v) + kEps;
+      if (gr >= 0 && gr < NR) x = __ldg(px + (rowmap ? (long long)__ldg(rowmap + gr) : gr) * V + v) + kEps;
       Ps[v * ld + r] = x;
     }
   }
@@ -131,6 +260,23 @@ __device__ __forceinline__ float window_valid(const uint8_t* __restrict__ mask, 
   if (row < 0 || row >= NR) return 0.f;
   int t = (int)(row % T);
   return (t <= T - n && __ldg(mask + row) != 0) ? 1.f : 0.f;
+}
+// the same in the packed index space: one sequence, a flag per row
+__device__ __forceinline__ float window_valid_packed(const uint8_t* __restrict__ wflag, long long row, long long NRp) {
+  return (row >= 0 && row < NRp && __ldg(wflag + row) != 0) ? 1.f : 0.f;
+}
+// tile height for `rows` rows over `grid` CTAs whose lanes own 32 R windows: the smallest number of equal slices per CTA
+// that fits the lanes, not finer than kMinTileRowsDev (a tile costs a full trie walk whatever its height)
+__device__ __forceinline__ int device_tile_rows(long long rows, int grid, int cap) {
+  long long ts = cap;
+  for (long long k = 1;; ++k) {
+    ts = (rows + (long long)grid * k - 1) / ((long long)grid * k);
+    if (ts <= cap) break;
+  }
+  const int kMinTileRowsDev = 128;
+  if (ts < kMinTileRowsDev) ts = kMinTileRowsDev < cap ? kMinTileRowsDev : cap;
+  if (ts < 1) ts = 1;
+  return (int)ts;
 }
 
 // ---------------------------------------------------------------------------
@@ -260,8 +406,13 @@ template <int DEPTH, int R, bool ACC_SMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restrict__ px,
                        const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int tsa, int n_tiles,
-                       int n_leaves, float* __restrict__ part, int* __restrict__ part_cnt) {
+                       int n_leaves, float* __restrict__ part, int* __restrict__ part_cnt, const PackView pk) {
   constexpr int TS = 32 * R;
+  if (pk.rowmap) {   // packed rows: their number, and with it the tiling, is known on the device only
+    NR = pk.counts[0];
+    ts = device_tile_rows(NR, gridDim.x, tsa < TS ? tsa : TS);
+    n_tiles = (int)((NR + ts - 1) / ts);
+  }
   extern __shared__ float smem[];
   // tsa = tile rows the shared-memory layout is cut for: TS, or (R = 1, wide vocabularies) 16 / 8 / 4 -- then only the
   // first tsa lanes own windows; the others read past their phone's row (finite values of the next row or of the arrays
@@ -290,15 +441,15 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * ts;
     __syncthreads();  // the previous tile is fully consumed (and acc / s_cnt are initialised)
-    stage_tile(Ps, ld, px, row0, ts + n - 1, tsa + n - 1, NR, V);
+    stage_tile(Ps, ld, px, row0, ts + n - 1, tsa + n - 1, NR, V, pk.rowmap);
     int my_valid = 0;
     for (int i = threadIdx.x; i < TS; i += kThreads) {   // warp-uniform trip count: TS is a multiple of 32
       const long long row = row0 + i;
       const bool in_tile = i < ts && row < NR;
-      const float ok = in_tile ? window_valid(mask, row, NR, T, n) : 0.f;
+      const float ok = !in_tile ? 0.f : pk.rowmap ? window_valid_packed(pk.wflag, row, NR) : window_valid(mask, row, NR, T, n);
       wm[i] = ok;
       my_valid |= ok != 0.f;
-      const int in_mask = in_tile && __ldg(mask + row) != 0;
+      const int in_mask = in_tile && !pk.rowmap && __ldg(mask + row) != 0;   // (packed: the pack kernels counted the frames)
       // N counts every valid frame (EODM.py:20), the order-0 columns count valid windows
       const unsigned bm = __ballot_sync(0xffffffffu, in_mask), bw = __ballot_sync(0xffffffffu, ok != 0.f);
       if (lane == 0) {
@@ -362,7 +513,7 @@ __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __
                                                                  int n_leaves, const int32_t* __restrict__ perm,
                                                                  const int32_t* __restrict__ order0, int n_order0,
                                                                  float* __restrict__ S, float* __restrict__ N,
-                                                                 float* __restrict__ W) {
+                                                                 float* __restrict__ W, const int* __restrict__ pack_counts) {
   __shared__ float red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int leaf = blockIdx.x * 32 + x;
@@ -385,7 +536,7 @@ __global__ void __launch_bounds__(256) eodm_counts_finish_kernel(const float* __
       cw += part_cnt[2 * c + 1];
     }
     if (i < n_order0) S[order0[i]] = (float)cw;
-    if (i == 0 && N) N[0] = (float)cn;
+    if (i == 0 && N) N[0] = pack_counts ? (float)pack_counts[1] : (float)cn;   // packed rows: frames counted by the pack kernels
     if (i == 0 && W) W[0] = (float)cw;   // the truncated denominator of the legacy partial sums (models/EODM.py:49-50)
   }
 }
@@ -511,8 +662,13 @@ template <int DEPTH, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __restrict__ px,
                        const uint8_t* __restrict__ mask, long long NR, int T, int V, int n, int ts, int tsa, int n_tiles,
-                       float* __restrict__ dpx, int accumulate) {
+                       float* __restrict__ dpx, int accumulate, const PackView pk) {
   constexpr int TS = 32 * R;
+  if (pk.rowmap) {
+    NR = pk.counts[0];
+    ts = device_tile_rows(NR, gridDim.x, tsa < TS ? tsa : TS);
+    n_tiles = (int)((NR + ts - 1) / ts);
+  }
   extern __shared__ float smem[];
   const int ld = odd_ld(tsa + 2 * (n - 1));   // tsa: see eodm_counts_fwd_kernel
   const int ldo = odd_ld(tsa);
@@ -538,12 +694,14 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * ts;
     __syncthreads();
-    stage_tile(Ps, ld, px, row0 - (n - 1), ts + 2 * (n - 1), tsa + 2 * (n - 1), NR, V);
+    stage_tile(Ps, ld, px, row0 - (n - 1), ts + 2 * (n - 1), tsa + 2 * (n - 1), NR, V, pk.rowmap);
     for (int i = threadIdx.x; i < V * ldo; i += kThreads) dP[i] = 0.f;
     int my_valid = 0;
     for (int i = threadIdx.x; i < TS + n - 1; i += kThreads) {
       // window i starts at row row0-(n-1)+i; it feeds output rows of this tile only if it starts before row0+ts
-      const float ok = (i < ts + n - 1) ? window_valid(mask, row0 - (n - 1) + i, NR, T, n) : 0.f;
+      const float ok = !(i < ts + n - 1) ? 0.f
+                       : pk.rowmap   ? window_valid_packed(pk.wflag, row0 - (n - 1) + i, NR)
+                                     : window_valid(mask, row0 - (n - 1) + i, NR, T, n);
       wm[i] = ok;
       my_valid |= ok != 0.f;
     }
@@ -627,6 +785,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
         int r = idx / V, v = idx - r * V;
         long long gr = row0 + r;
         if (gr < NR) {
+          if (pk.rowmap) gr = __ldg(pk.rowmap + gr);           // packed rows scatter back to their padded places
           if (accumulate) dpx[gr * V + v] += dP[v * ldo + r];   // several tables over one posterior sequence
           else dpx[gr * V + v] = dP[v * ldo + r];
         }
@@ -723,7 +882,7 @@ bool choose_tiling(const eodm_table* t, long long NR, FitFn fits, Tiling* out, b
 template <int DEPTH, int R>
 cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
                           const Tiling& tl, int n_leaves, bool acc_smem, float* part, int* part_cnt, size_t smem,
-                          cudaStream_t st) {
+                          cudaStream_t st, const PackView& pk) {
   if constexpr (!(R <= 8 || DEPTH <= 5)) {
     return cudaErrorInvalidValue;
   } else {
@@ -732,12 +891,12 @@ cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mas
       auto k = eodm_counts_fwd_kernel<DEPTH, R, true>;
       e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt);
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt, pk);
     } else {
       auto k = eodm_counts_fwd_kernel<DEPTH, R, false>;
       e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt);
+      k<<<tl.grid, kThreads, smem, st>>>(tr, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, n_leaves, part, part_cnt, pk);
     }
     return cudaGetLastError();
   }
@@ -745,14 +904,14 @@ cudaError_t launch_fwd_dr(const TrieArg& tr, const float* px, const uint8_t* mas
 
 template <int DEPTH, int R>
 cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask, long long NR, int T, int V, int n,
-                          const Tiling& tl, float* dpx, int accumulate, size_t smem, cudaStream_t st) {
+                          const Tiling& tl, float* dpx, int accumulate, size_t smem, cudaStream_t st, const PackView& pk) {
   if constexpr (!(R <= 8 || DEPTH <= 5)) {
     return cudaErrorInvalidValue;
   } else {
     auto k = eodm_counts_bwd_kernel<DEPTH, R>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, dpx, accumulate);
+    k<<<tl.grid, kThreads, smem, st>>>(a, px, mask, NR, T, V, n, tl.ts, tl.tsa, tl.n_tiles, dpx, accumulate, pk);
     return cudaGetLastError();
   }
 }
@@ -809,10 +968,56 @@ static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, flo
   *ng = (uint2*)p;
 }
 
+// workspace of the row packing for a [B][T] batch: [rowmap: NR i32][wflag: NR u8][block counts, block frames: 2 x ceil(NR /
+// 1024) i32][packed rows, frames: 2 i32]
+size_t eodm_pack_workspace_bytes(long long NR) {
+  const size_t n_blk = (size_t)((NR + kPackRows - 1) / kPackRows);
+  return up256((size_t)NR * sizeof(int)) + up256((size_t)NR) + 2 * up256(n_blk * sizeof(int)) + 256 + 256;
+}
+
+int g_packing = 1;   // test hook (eodm_debug_set_packing): 0 = walk the padded rows as round 1 did
+
+static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack_ws, cudaStream_t st, PackView* pk) {
+  pk->rowmap = nullptr;
+  pk->wflag = nullptr;
+  pk->counts = nullptr;
+  if (!pack_ws || !g_packing || g_force_ts > 0 || NR > 0x7fffffffLL) return EODM_OK;   // (a pinned tile height: padded rows)
+  char* p = (char*)(((uintptr_t)pack_ws + 255) & ~(uintptr_t)255);
+  const int n_blk = (int)((NR + kPackRows - 1) / kPackRows);
+  int* rowmap = (int*)p;
+  p += up256((size_t)NR * sizeof(int));
+  uint8_t* wflag = (uint8_t*)p;
+  p += up256((size_t)NR);
+  int* bsum = (int*)p;
+  p += up256((size_t)n_blk * sizeof(int));
+  int* bfr = (int*)p;
+  p += up256((size_t)n_blk * sizeof(int));
+  int* counts = (int*)p;
+  eodm_pack_count_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, bfr);
+  eodm_pack_scan_kernel<<<1, 1024, 0, st>>>(bsum, bfr, n_blk, counts);
+  eodm_pack_fill_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, rowmap, wflag);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    eodm_set_error("row packing kernels failed to launch: %s", cudaGetErrorString(e));
+    return EODM_ECUDA;
+  }
+  pk->rowmap = rowmap;
+  pk->wflag = wflag;
+  pk->counts = counts;
+  return EODM_OK;
+}
+
+extern "C" void eodm_debug_set_packing(int on) { g_packing = on; }
+
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           float* W, void* ws, cudaStream_t st) {
+                           float* W, void* ws, cudaStream_t st, void* pack_ws) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
+  PackView pk;
+  {
+    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
+    if (rc != EODM_OK) return rc;
+  }
   const int n_leaves = t->trie[0].n_leaves;
   bool acc_smem = true;
   Tiling tl;
@@ -843,7 +1048,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   tr.total_cost = t->trie[0].total_cost;
   for (int l = 0; l < EODM_MAX_N; ++l) tr.off[l] = (l < n) ? t->trie[0].pos[l] : 0;
   cudaError_t e;
-#define CALL(D, R) launch_fwd_dr<D, R>(tr, px, mask, NR, T, V, n, tl, n_leaves, acc_smem, part, cnt, smem, st)
+#define CALL(D, R) launch_fwd_dr<D, R>(tr, px, mask, NR, T, V, n, tl, n_leaves, acc_smem, part, cnt, smem, st, pk)
   EODM_DISPATCH(n, tl.R, CALL)
 #undef CALL
   if (e != cudaSuccess) {
@@ -855,7 +1060,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   if (fg < 1) fg = 1;
   const int fb = 256;
   eodm_counts_finish_kernel<<<fg, fb, 0, st>>>(part, cnt, tl.grid, n_leaves, t->trie[0].perm, t->d_order0,
-                                               t->n_order0, S, N, W);
+                                               t->n_order0, S, N, W, pk.counts);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("eodm_counts_finish_kernel launch failed: %s", cudaGetErrorString(e));
@@ -865,9 +1070,19 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 }
 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                           float* dpx, void* ws, cudaStream_t st, int accumulate) {
+                           float* dpx, void* ws, cudaStream_t st, int accumulate, void* pack_ws) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
+  PackView pk;
+  {
+    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
+    if (rc != EODM_OK) return rc;
+    // rows outside every window are not visited any more: their gradient is zero
+    if (pk.rowmap && !accumulate && cudaMemsetAsync(dpx, 0, sizeof(float) * (size_t)NR * V, st) != cudaSuccess) {
+      eodm_set_error("cudaMemsetAsync failed");
+      return EODM_ECUDA;
+    }
+  }
   Tiling tl;
   auto fits = [&](int R) { return bwd_smem_bytes(R < 0 ? 1 : R, V, n, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
   if (!choose_tiling(t, NR, fits, &tl)) {
@@ -910,7 +1125,7 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     tr.total_cost = h.total_cost;
     for (int l = 0; l < EODM_MAX_N; ++l) tr.off[l] = (l < n) ? h.pos[l] - j + (n - 1) : 0;
   }
-#define CALL(D, R) launch_bwd_dr<D, R>(a, px, mask, NR, T, V, n, tl, dpx, accumulate, smem, st)
+#define CALL(D, R) launch_bwd_dr<D, R>(a, px, mask, NR, T, V, n, tl, dpx, accumulate, smem, st, pk)
   EODM_DISPATCH(n, tl.R, CALL)
 #undef CALL
   if (e != cudaSuccess) {
