@@ -105,8 +105,10 @@ extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
   return counts_ws_aligned(t) + tcb_ws_aligned(t) + tcf_ws_aligned(t) + eodm_pack_workspace_bytes(NR);
 }
 
-extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
-                               float* N, void* ws, void* stream) {
+// rows_host (sessions): a pinned host word through which the walk learns, one step late, how many rows survive the
+// packing of the session's batches -- see plan_rows in counts.cu
+static int counts_fwd_any(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
+                          void* ws, void* stream, int* rows_host) {
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
@@ -114,7 +116,12 @@ extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8
   if (path == 3)
     return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tcb_ws_aligned(t),
                            (cudaStream_t)stream);
-  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream, pack_ws_of(t, ws));
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream, pack_ws_of(t, ws), rows_host);
+}
+
+extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
+                               float* N, void* ws, void* stream) {
+  return counts_fwd_any(t, px, mask, B, T, S, N, ws, stream, nullptr);
 }
 
 // The reference's older multi-device step (models/EODM.py:28-52, main_es.py:135,331-335) returns UN-normalised
@@ -128,14 +135,15 @@ extern "C" int eodm_counts_partial(const eodm_table* t, const float* px, const u
 }
 
 static int counts_bwd_any(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                          float* dpx, void* ws, void* stream, int accumulate) {
+                          float* dpx, void* ws, void* stream, int accumulate, int* rows_host = nullptr) {
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
   if (use_tensor_bwd(t))
     return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t),
                            (cudaStream_t)stream, accumulate);
-  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate, pack_ws_of(t, ws));
+  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate, pack_ws_of(t, ws),
+                                rows_host);
 }
 
 extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
@@ -296,6 +304,7 @@ struct eodm_session {
   uint8_t* mask;
   void* ws;
   eodm_peer* peer;   // when set: the exchange + loss run as one kernel over peer memory (peer.cu)
+  int* rows_host;    // pinned: packed row count of the previous batches (plan_rows in counts.cu)
   // submit/wait (two steps in flight): per-slot input / output buffers and events, allocated at the first submit;
   // px, dpx, counts, gS and the workspace are shared -- they are only touched on the in-order compute stream
   struct Slot {
@@ -316,6 +325,7 @@ static void session_free(eodm_session* s) {
   void* ptrs[] = {s->logits, s->px, s->dpx, s->dlogits, s->counts, s->counts2, s->py, s->gS, s->loss, s->mask, s->ws};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (s->rows_host) cudaFreeHost(s->rows_host);
   for (cudaEvent_t ev : {s->ev_in[0], s->ev_in[1], s->ev_out[0], s->ev_out[1], s->ev_done})
     if (ev) cudaEventDestroy(ev);
   for (auto& sl : s->slot) {
@@ -367,6 +377,8 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
   if (e == cudaSuccess) e = cudaMalloc(&s->ws, eodm_workspace_bytes(t, maxB, maxT));
   if (e == cudaSuccess) e = cudaMemset(s->ws, 0, eodm_workspace_bytes(t, maxB, maxT));   // the tail kernel's ticket starts at 0
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->rows_host, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) memset(s->rows_host, 0, 64);
   if (e == cudaSuccess) e = cudaMemcpy(s->py, py_host, (size_t)t->K * sizeof(float), cudaMemcpyHostToDevice);
   if (prev >= 0) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -411,7 +423,7 @@ static int session_exchange_and_loss(eodm_session* s, float* counts, void* comm,
 
 static int session_vjp(eodm_session* s, const float* px, const uint8_t* mask, int B, int T, float* dpx, cudaStream_t st,
                        bool image_ready) {
-  if (!image_ready) return eodm_counts_bwd(s->t, px, mask, B, T, s->gS, dpx, s->ws, st);
+  if (!image_ready) return counts_bwd_any(s->t, px, mask, B, T, s->gS, dpx, s->ws, st, 0, s->rows_host + 1);
   const int rc = check_batch(s->t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   return eodm_tcb_launch(s->t, px, mask, B, T, s->gS, dpx, session_tcb_ws(s), st, 0, 1);
@@ -442,7 +454,7 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
               : eodm_tc_tail_launch(t, &parts, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st);
     image_ready = true;
   } else {
-    if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px, mask, B, T, S, N, s->ws, st);
+    if (rc == EODM_OK) rc = counts_fwd_any(t, s->px, mask, B, T, S, N, s->ws, st, s->rows_host);
     if (rc == EODM_OK) rc = session_exchange_and_loss(s, s->counts, comm, loss, dlogits != nullptr, st, &image_ready);
   }
   if (rc == EODM_OK && dlogits) rc = session_vjp(s, s->px, mask, B, T, s->dpx, st, image_ready);
@@ -657,6 +669,7 @@ struct eodm_multi {
   float *px, *dpx, *counts, *gS, *py;   // gS, py: the K_o vectors back to back (offset off[o] - o)
   unsigned* done;
   void* ws;
+  int* rows_host;            // pinned [2 n]: packed row counts of the previous batches, per table, forward / VJP
   EodmMultiLossArgs la;
 };
 
@@ -666,6 +679,7 @@ static void multi_free(eodm_multi* m) {
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->px); cudaFree(m->dpx); cudaFree(m->counts); cudaFree(m->gS); cudaFree(m->py); cudaFree(m->done); cudaFree(m->ws);
+  if (m->rows_host) cudaFreeHost(m->rows_host);
   if (prev >= 0) cudaSetDevice(prev);
   delete m;
 }
@@ -715,6 +729,8 @@ extern "C" int eodm_multi_create(const eodm_table* const* tables, const float* c
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->py, (size_t)total * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->done, 256);
   if (e == cudaSuccess) e = cudaMemset(m->done, 0, 256);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->rows_host, sizeof(int) * 2 * EODM_MULTI_MAX, cudaHostAllocDefault);
+  if (e == cudaSuccess) memset(m->rows_host, 0, sizeof(int) * 2 * EODM_MULTI_MAX);
   if (e == cudaSuccess) e = cudaMalloc(&m->ws, ws_bytes + 256);
   for (int o = 0; o < n_tables && e == cudaSuccess; ++o)
     e = cudaMemcpy(m->py + (m->off[o] - o), py_host[o], (size_t)tables[o]->K * sizeof(float), cudaMemcpyHostToDevice);
@@ -750,12 +766,14 @@ extern "C" int eodm_multi_step_device(eodm_multi* m, const float* logits, const 
   const int64_t rows = (int64_t)B * T;
   int rc = eodm_softmax_fwd_launch(logits, rows, m->V, m->px, st);
   for (int o = 0; o < m->n && rc == EODM_OK; ++o)
-    rc = eodm_counts_fwd(m->t[o], m->px, mask, B, T, m->counts + m->off[o], m->counts + m->off[o] + m->t[o]->K, m->ws, st);
+    rc = counts_fwd_any(m->t[o], m->px, mask, B, T, m->counts + m->off[o], m->counts + m->off[o] + m->t[o]->K, m->ws, st,
+                        m->rows_host + 2 * o);
   // ONE collective for every table's [S, N]: the buffer is contiguous
   if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, m->counts, m->total - 1, m->counts + m->total - 1, st);
   if (rc == EODM_OK) rc = eodm_loss_multi_launch(m->la, 1e-15f, loss_out, m->done, dlogits != nullptr, st);
   for (int o = 0; o < m->n && rc == EODM_OK && dlogits; ++o)
-    rc = counts_bwd_any(m->t[o], m->px, mask, B, T, m->gS + (m->off[o] - o), m->dpx, m->ws, st, o > 0 ? 1 : 0);
+    rc = counts_bwd_any(m->t[o], m->px, mask, B, T, m->gS + (m->off[o] - o), m->dpx, m->ws, st, o > 0 ? 1 : 0,
+                        m->rows_host + 2 * o + 1);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(m->px, m->dpx, rows, m->V, dlogits, st);
   return rc;
 }

@@ -824,7 +824,7 @@ size_t bwd_smem_bytes(int R, int V, int n, int tsa = 0) {
 }
 
 // windows-per-lane variants compiled for a given trie depth (register budget: R floats per level)
-constexpr int kRs[] = {12, 11, 8, 4, 1};
+constexpr int kRs[] = {12, 11, 10, 8, 6, 4, 1};
 __host__ inline bool r_allowed(int depth, int R) { return R <= 8 || depth <= 5; }
 
 // Tile height: the smallest number of equal row slices per SM such that a slice fits the lanes.
@@ -920,7 +920,9 @@ cudaError_t launch_bwd_dr(const BwdArgs& a, const float* px, const uint8_t* mask
   switch (R) {                                        \
     case 12: e = CALL(D, 12); break;                  \
     case 11: e = CALL(D, 11); break;                  \
+    case 10: e = CALL(D, 10); break;                  \
     case 8: e = CALL(D, 8); break;                    \
+    case 6: e = CALL(D, 6); break;                    \
     case 4: e = CALL(D, 4); break;                    \
     default: e = CALL(D, 1); break;                   \
   }
@@ -1009,8 +1011,19 @@ static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack
 
 extern "C" void eodm_debug_set_packing(int on) { g_packing = on; }
 
+// Which windows-per-lane variant to launch is decided on the host, but the number of packed rows is known on the device
+// only.  A caller that repeats similar batches (a session) passes a pinned host word: this launch copies its packed row
+// count there (asynchronously, on the stream) and plans with whatever an earlier launch left -- a stale hint costs
+// speed, never correctness (the tile height is computed on the device and capped by the launched variant).
+static long long plan_rows(long long NR, const PackView& pk, int* rows_host, cudaStream_t st) {
+  if (!pk.rowmap || !rows_host) return NR;
+  const int hint = *(volatile int*)rows_host;
+  cudaMemcpyAsync(rows_host, pk.counts, sizeof(int), cudaMemcpyDeviceToHost, st);
+  return (hint > 0 && hint <= NR) ? hint : NR;
+}
+
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           float* W, void* ws, cudaStream_t st, void* pack_ws) {
+                           float* W, void* ws, cudaStream_t st, void* pack_ws, int* rows_host) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   PackView pk;
@@ -1018,6 +1031,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
     if (rc != EODM_OK) return rc;
   }
+  const long long NRplan = plan_rows(NR, pk, rows_host, st);
   const int n_leaves = t->trie[0].n_leaves;
   bool acc_smem = true;
   Tiling tl;
@@ -1025,9 +1039,9 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   auto fits_s = [&](int R) { return fwd_smem_bytes(R < 0 ? 1 : R, V, n, n_leaves, true, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
   auto fits_g = [&](int R) { return fwd_smem_bytes(R < 0 ? 1 : R, V, n, n_leaves, false, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
   // prefer shared-memory accumulators unless they force a much smaller tile than global ones would allow
-  if (!choose_tiling(t, NR, fits_s, &tl, false)) {
+  if (!choose_tiling(t, NRplan, fits_s, &tl, false)) {
     acc_smem = false;
-    if (!choose_tiling(t, NR, fits_g, &tl)) {
+    if (!choose_tiling(t, NRplan, fits_g, &tl)) {
       eodm_set_error("trie path: not even a [V=%d] x 4-row tile fits in %d bytes of shared memory", V, kMaxSmem);
       return EODM_EUNSUPPORTED;
     }
@@ -1070,7 +1084,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 }
 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                           float* dpx, void* ws, cudaStream_t st, int accumulate, void* pack_ws) {
+                           float* dpx, void* ws, cudaStream_t st, int accumulate, void* pack_ws, int* rows_host) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   PackView pk;
@@ -1085,7 +1099,7 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   }
   Tiling tl;
   auto fits = [&](int R) { return bwd_smem_bytes(R < 0 ? 1 : R, V, n, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
-  if (!choose_tiling(t, NR, fits, &tl)) {
+  if (!choose_tiling(t, plan_rows(NR, pk, rows_host, st), fits, &tl)) {
     eodm_set_error("trie path: not even a [V=%d] x 4-row tile fits in %d bytes of shared memory", V, kMaxSmem);
     return EODM_EUNSUPPORTED;
   }
