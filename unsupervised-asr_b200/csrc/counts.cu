@@ -1031,6 +1031,7 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
     const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
     if (rc != EODM_OK) return rc;
   }
+  if (!rows_host) rows_host = t->rows_host;   // no caller-side hint: the table's own
   const long long NRplan = plan_rows(NR, pk, rows_host, st);
   const int n_leaves = t->trie[0].n_leaves;
   bool acc_smem = true;
@@ -1099,7 +1100,7 @@ int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* 
   }
   Tiling tl;
   auto fits = [&](int R) { return bwd_smem_bytes(R < 0 ? 1 : R, V, n, R < 0 ? -R : 0) <= (size_t)kMaxSmem; };
-  if (!choose_tiling(t, plan_rows(NR, pk, rows_host, st), fits, &tl)) {
+  if (!choose_tiling(t, plan_rows(NR, pk, rows_host ? rows_host : t->rows_host, st), fits, &tl)) {
     eodm_set_error("trie path: not even a [V=%d] x 4-row tile fits in %d bytes of shared memory", V, kMaxSmem);
     return EODM_EUNSUPPORTED;
   }

@@ -189,6 +189,7 @@ void eodm_free_table(eodm_table* t) {
   cudaGetDevice(&prev);
   if (t->device >= 0) cudaSetDevice(t->device);
   for (void* p : t->allocs) cudaFree(p);
+  if (t->rows_host) cudaFreeHost(t->rows_host);
   if (prev >= 0) cudaSetDevice(prev);
   delete t;
 }
@@ -218,6 +219,7 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
   t->d_inv_zj = nullptr;
   t->d_order = nullptr;
   t->sm_count = 0;
+  t->rows_host = nullptr;
   t->d_nodes_all = nullptr;
   t->d_node_z = nullptr;
   t->d_perm_all = nullptr;
@@ -465,6 +467,10 @@ int eodm_build_table(const int32_t* ids, int K, int n, int V, int device, eodm_t
         eodm_set_error("cudaDeviceGetAttribute(MultiProcessorCount) failed: %s", cudaGetErrorString(ce));
         rc = EODM_ECUDA;
       }
+    }
+    if (rc == EODM_OK) {
+      if (cudaHostAlloc((void**)&t->rows_host, 64, cudaHostAllocDefault) == cudaSuccess) memset(t->rows_host, 0, 64);
+      else t->rows_host = nullptr;   // only a planning hint: do without
     }
   }
   if (prev >= 0) cudaSetDevice(prev);

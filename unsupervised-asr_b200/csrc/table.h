@@ -96,6 +96,8 @@ struct eodm_table {
   int32_t* d_inv_zj;          // [nnz] packed z * EODM_MAX_N + j
   uint8_t* d_order;           // [K]
   int sm_count;               // multiprocessors of `device`
+  int* rows_host;             // pinned host word: rows the walk's packing kept for the last batches (a planning hint for
+                              // callers that bring none of their own -- plan_rows in counts.cu); nullptr: host-only table
   // all tries' node streams back to back (each followed by one zero word of slack), and for every
   // node the n-gram index z that ends there (-1: none): the backward pass pairs nodes with dloss/dS[z]
   uint32_t* d_nodes_all;
