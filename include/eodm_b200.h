@@ -74,7 +74,9 @@ int eodm_table_to_dense(const eodm_table* t, float* kernel_host);
 
 /* ---- expected n-gram counts (replaces conv_op + masked reduce, models/EODM.py:14,18-20) ---- */
 
-/* Bytes of caller-owned scratch `ws` that eodm_counts_fwd/bwd need for a [B,T,V] batch. */
+/* Bytes of caller-owned scratch `ws` that eodm_counts_fwd/bwd need for a [B,T,V] batch.  Grows with B*T (5 bytes per
+ * frame: the walk lists the rows that take part in a valid window and skips the padding of ragged batches row by row);
+ * a `ws` sized for a larger batch serves every smaller one. */
 size_t eodm_workspace_bytes(const eodm_table* t, int B, int T);
 
 /* S[z] = sum_{b, t <= T-n} mask[b,t] * prod_j (px[b,t+j,ids[z,j]] + 1e-15)   (f32[K])
