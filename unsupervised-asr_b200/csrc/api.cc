@@ -107,8 +107,9 @@ extern "C" size_t eodm_workspace_bytes(const eodm_table* t, int B, int T) {
 
 // rows_host (sessions): a pinned host word through which the walk learns, one step late, how many rows survive the
 // packing of the session's batches -- see plan_rows in counts.cu
+// shared_pack / packed_n: a packing of this batch made once for several walks (eodm_pack_rows_launch) and where it lies
 static int counts_fwd_any(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                          void* ws, void* stream, int* rows_host) {
+                          void* ws, void* stream, int* rows_host, void* shared_pack = nullptr, int packed_n = 0) {
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(S && ws, EODM_EINVAL, "null pointer");
@@ -116,7 +117,8 @@ static int counts_fwd_any(const eodm_table* t, const float* px, const uint8_t* m
   if (path == 3)
     return eodm_tcf_launch(t, px, mask, B, T, S, N, (char*)ws + counts_ws_aligned(t) + tcb_ws_aligned(t),
                            (cudaStream_t)stream);
-  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream, pack_ws_of(t, ws), rows_host);
+  return eodm_counts_fwd_launch(t, px, mask, B, T, S, N, nullptr, ws, (cudaStream_t)stream,
+                                shared_pack ? shared_pack : pack_ws_of(t, ws), rows_host, shared_pack ? packed_n : 0);
 }
 
 extern "C" int eodm_counts_fwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S,
@@ -135,15 +137,16 @@ extern "C" int eodm_counts_partial(const eodm_table* t, const float* px, const u
 }
 
 static int counts_bwd_any(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                          float* dpx, void* ws, void* stream, int accumulate, int* rows_host = nullptr) {
+                          float* dpx, void* ws, void* stream, int accumulate, int* rows_host = nullptr,
+                          void* shared_pack = nullptr, int packed_n = 0) {
   int rc = check_batch(t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   REQUIRE(gS && dpx && ws, EODM_EINVAL, "null pointer");
   if (use_tensor_bwd(t))
     return eodm_tcb_launch(t, px, mask, B, T, gS, dpx, (char*)ws + counts_ws_aligned(t),
                            (cudaStream_t)stream, accumulate);
-  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate, pack_ws_of(t, ws),
-                                rows_host);
+  return eodm_counts_bwd_launch(t, px, mask, B, T, gS, dpx, ws, (cudaStream_t)stream, accumulate,
+                                shared_pack ? shared_pack : pack_ws_of(t, ws), rows_host, shared_pack ? packed_n : 0);
 }
 
 extern "C" int eodm_counts_bwd(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T,
@@ -421,9 +424,12 @@ static int session_exchange_and_loss(eodm_session* s, float* counts, void* comm,
   return eodm_loss_launch(counts, counts + K, s->py, K, 1e-15f, loss, need_grad ? s->gS : nullptr, st);
 }
 
+// reuse_pack: the forward of the SAME batch was the walk and ran last on this workspace -- its row packing is still there
 static int session_vjp(eodm_session* s, const float* px, const uint8_t* mask, int B, int T, float* dpx, cudaStream_t st,
-                       bool image_ready) {
-  if (!image_ready) return counts_bwd_any(s->t, px, mask, B, T, s->gS, dpx, s->ws, st, 0, s->rows_host + 1);
+                       bool image_ready, bool reuse_pack = false) {
+  if (!image_ready)
+    return counts_bwd_any(s->t, px, mask, B, T, s->gS, dpx, s->ws, st, 0, s->rows_host + 1,
+                          reuse_pack ? pack_ws_of(s->t, s->ws) : nullptr, reuse_pack ? s->t->n : 0);
   const int rc = check_batch(s->t, px, mask, B, T);
   if (rc != EODM_OK) return rc;
   return eodm_tcb_launch(s->t, px, mask, B, T, s->gS, dpx, session_tcb_ws(s), st, 0, 1);
@@ -457,7 +463,7 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
     if (rc == EODM_OK) rc = counts_fwd_any(t, s->px, mask, B, T, S, N, s->ws, st, s->rows_host);
     if (rc == EODM_OK) rc = session_exchange_and_loss(s, s->counts, comm, loss, dlogits != nullptr, st, &image_ready);
   }
-  if (rc == EODM_OK && dlogits) rc = session_vjp(s, s->px, mask, B, T, s->dpx, st, image_ready);
+  if (rc == EODM_OK && dlogits) rc = session_vjp(s, s->px, mask, B, T, s->dpx, st, image_ready, fwd_path(t) == 0);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(s->px, s->dpx, rows, t->V, dlogits, st);
   return rc;
 }
@@ -669,6 +675,8 @@ struct eodm_multi {
   float *px, *dpx, *counts, *gS, *py;   // gS, py: the K_o vectors back to back (offset off[o] - o)
   unsigned* done;
   void* ws;
+  void* pack_ws;             // the row packing of the step's batch, made once for every table's walks
+  int n_max;                 // largest kernel_size among the tables
   int* rows_host;            // pinned [2 n]: packed row counts of the previous batches, per table, forward / VJP
   EodmMultiLossArgs la;
 };
@@ -678,7 +686,7 @@ static void multi_free(eodm_multi* m) {
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
-  cudaFree(m->px); cudaFree(m->dpx); cudaFree(m->counts); cudaFree(m->gS); cudaFree(m->py); cudaFree(m->done); cudaFree(m->ws);
+  cudaFree(m->px); cudaFree(m->dpx); cudaFree(m->counts); cudaFree(m->gS); cudaFree(m->py); cudaFree(m->done); cudaFree(m->ws); cudaFree(m->pack_ws);
   if (m->rows_host) cudaFreeHost(m->rows_host);
   if (prev >= 0) cudaSetDevice(prev);
   delete m;
@@ -729,6 +737,8 @@ extern "C" int eodm_multi_create(const eodm_table* const* tables, const float* c
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->py, (size_t)total * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->done, 256);
   if (e == cudaSuccess) e = cudaMemset(m->done, 0, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&m->pack_ws, eodm_pack_workspace_bytes((long long)maxB * maxT));
+  m->n_max = n_max;
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->rows_host, sizeof(int) * 2 * EODM_MULTI_MAX, cudaHostAllocDefault);
   if (e == cudaSuccess) memset(m->rows_host, 0, sizeof(int) * 2 * EODM_MULTI_MAX);
   if (e == cudaSuccess) e = cudaMalloc(&m->ws, ws_bytes + 256);
@@ -765,15 +775,19 @@ extern "C" int eodm_multi_step_device(eodm_multi* m, const float* logits, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = (int64_t)B * T;
   int rc = eodm_softmax_fwd_launch(logits, rows, m->V, m->px, st);
+  // one row packing for all the walks of this step (three launches instead of three per walk)
+  const int pn = m->n_max <= 8 ? m->n_max : 0;
+  if (rc == EODM_OK && pn) rc = eodm_pack_rows_launch(mask, B, T, pn, m->pack_ws, st);
+  void* sp = pn ? m->pack_ws : nullptr;
   for (int o = 0; o < m->n && rc == EODM_OK; ++o)
     rc = counts_fwd_any(m->t[o], m->px, mask, B, T, m->counts + m->off[o], m->counts + m->off[o] + m->t[o]->K, m->ws, st,
-                        m->rows_host + 2 * o);
+                        m->rows_host + 2 * o, sp, pn);
   // ONE collective for every table's [S, N]: the buffer is contiguous
   if (rc == EODM_OK && comm) rc = eodm_allreduce_counts(comm, m->counts, m->total - 1, m->counts + m->total - 1, st);
   if (rc == EODM_OK) rc = eodm_loss_multi_launch(m->la, 1e-15f, loss_out, m->done, dlogits != nullptr, st);
   for (int o = 0; o < m->n && rc == EODM_OK && dlogits; ++o)
     rc = counts_bwd_any(m->t[o], m->px, mask, B, T, m->gS + (m->off[o] - o), m->dpx, m->ws, st, o > 0 ? 1 : 0,
-                        m->rows_host + 2 * o + 1);
+                        m->rows_host + 2 * o + 1, sp, pn);
   if (rc == EODM_OK && dlogits) rc = eodm_softmax_bwd_launch(m->px, m->dpx, rows, m->V, dlogits, st);
   return rc;
 }

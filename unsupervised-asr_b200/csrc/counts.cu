@@ -74,20 +74,25 @@ struct BwdArgs {
 // through it when they write one; the tile height is chosen on the device from the packed row count.
 struct PackView {
   const int* rowmap;        // [NR] packed row -> padded row (nullptr: no packing)
-  const uint8_t* wflag;     // [NR] a window may start at this packed row
+  const uint8_t* wflag;     // [NR] bit k-1: a window of kernel_size k may start at this packed row
   const int* counts;        // [0] packed rows, [1] valid frames (N of models/EODM.py:20)
+  unsigned bit;             // 1 << (kernel_size - 1) of the table being walked
 };
 constexpr int kPackRows = 1024;   // rows per block of the pack kernels (256 threads x 4 consecutive rows)
 
-__device__ __forceinline__ bool pack_wstart(const uint8_t* __restrict__ mask, long long row, int T, int n) {
-  return __ldg(mask + row) != 0 && (int)(row % T) <= T - n;
+// the window-start flags of a row for every kernel_size k = 1..8: bit k-1 = mask[b,t] and t <= T - k
+__device__ __forceinline__ unsigned pack_wbits(const uint8_t* __restrict__ mask, long long row, int T) {
+  if (__ldg(mask + row) == 0) return 0u;
+  const int room = T - (int)(row % T);   // rows from t to the end of the utterance's slot
+  return room >= 8 ? 0xffu : ((1u << room) - 1u);
 }
-// keep[row]: some window start lies in rows t-(n-1) .. t of the row's utterance
+// keep[row]: a valid frame lies in rows t-(n-1) .. t of the row's utterance -- every row a window of kernel_size <= n can
+// touch (and a few it cannot: the windows that would start in the last n-1 frames of a full-length utterance)
 __device__ __forceinline__ bool pack_keep(const uint8_t* __restrict__ mask, long long row, long long NR, int T, int n) {
   if (row >= NR) return false;
   const int t = (int)(row % T);
   for (int d = 0; d < n && d <= t; ++d)
-    if (pack_wstart(mask, row - d, T, n)) return true;
+    if (__ldg(mask + row - d) != 0) return true;
   return false;
 }
 __global__ void __launch_bounds__(256) eodm_pack_count_kernel(const uint8_t* __restrict__ mask, long long NR, int T, int n,
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(256) eodm_pack_fill_kernel(const uint8_t* __re
   for (int u = 0; u < 4; ++u)
     if (keep[u]) {
       rowmap[p] = (int)(r0 + u);
-      wflag[p] = pack_wstart(mask, r0 + u, T, n) ? 1 : 0;
+      wflag[p] = (uint8_t)pack_wbits(mask, r0 + u, T);
       ++p;
     }
 }
@@ -262,8 +267,9 @@ __device__ __forceinline__ float window_valid(const uint8_t* __restrict__ mask, 
   return (t <= T - n && __ldg(mask + row) != 0) ? 1.f : 0.f;
 }
 // the same in the packed index space: one sequence, a flag per row
-__device__ __forceinline__ float window_valid_packed(const uint8_t* __restrict__ wflag, long long row, long long NRp) {
-  return (row >= 0 && row < NRp && __ldg(wflag + row) != 0) ? 1.f : 0.f;
+__device__ __forceinline__ float window_valid_packed(const uint8_t* __restrict__ wflag, unsigned bit, long long row,
+                                                     long long NRp) {
+  return (row >= 0 && row < NRp && (__ldg(wflag + row) & bit) != 0) ? 1.f : 0.f;
 }
 // tile height for `rows` rows over `grid` CTAs whose lanes own 32 R windows: the smallest number of equal slices per CTA
 // that fits the lanes, not finer than kMinTileRowsDev (a tile costs a full trie walk whatever its height)
@@ -446,7 +452,7 @@ eodm_counts_fwd_kernel(const __grid_constant__ TrieArg tr, const float* __restri
     for (int i = threadIdx.x; i < TS; i += kThreads) {   // warp-uniform trip count: TS is a multiple of 32
       const long long row = row0 + i;
       const bool in_tile = i < ts && row < NR;
-      const float ok = !in_tile ? 0.f : pk.rowmap ? window_valid_packed(pk.wflag, row, NR) : window_valid(mask, row, NR, T, n);
+      const float ok = !in_tile ? 0.f : pk.rowmap ? window_valid_packed(pk.wflag, pk.bit, row, NR) : window_valid(mask, row, NR, T, n);
       wm[i] = ok;
       my_valid |= ok != 0.f;
       const int in_mask = in_tile && !pk.rowmap && __ldg(mask + row) != 0;   // (packed: the pack kernels counted the frames)
@@ -700,7 +706,7 @@ eodm_counts_bwd_kernel(const __grid_constant__ BwdArgs args, const float* __rest
     for (int i = threadIdx.x; i < TS + n - 1; i += kThreads) {
       // window i starts at row row0-(n-1)+i; it feeds output rows of this tile only if it starts before row0+ts
       const float ok = !(i < ts + n - 1) ? 0.f
-                       : pk.rowmap   ? window_valid_packed(pk.wflag, row0 - (n - 1) + i, NR)
+                       : pk.rowmap   ? window_valid_packed(pk.wflag, pk.bit, row0 - (n - 1) + i, NR)
                                      : window_valid(mask, row0 - (n - 1) + i, NR, T, n);
       wm[i] = ok;
       my_valid |= ok != 0.f;
@@ -979,11 +985,17 @@ size_t eodm_pack_workspace_bytes(long long NR) {
 
 int g_packing = 1;   // test hook (eodm_debug_set_packing): 0 = walk the padded rows as round 1 did
 
-static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack_ws, cudaStream_t st, PackView* pk) {
+// n: the table's kernel_size.  packed_n = 0: pack now, for this kernel_size; > 0: the region already holds the packing of
+// THIS batch made for kernel_size packed_n >= n (eodm_pack_rows_launch, or an earlier walk of the same step): its row
+// list is a superset of what this table needs and its flags carry a bit per kernel_size, so it is used as it is.
+static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack_ws, cudaStream_t st, PackView* pk,
+                     int packed_n = 0) {
   pk->rowmap = nullptr;
   pk->wflag = nullptr;
   pk->counts = nullptr;
-  if (!pack_ws || !g_packing || g_force_ts > 0 || NR > 0x7fffffffLL) return EODM_OK;   // (a pinned tile height: padded rows)
+  pk->bit = 1u << (n - 1);
+  if (!pack_ws || !g_packing || g_force_ts > 0 || NR > 0x7fffffffLL || n > 8) return EODM_OK;   // (a pinned tile height: padded rows)
+  if (packed_n > 0 && packed_n < n) packed_n = 0;
   char* p = (char*)(((uintptr_t)pack_ws + 255) & ~(uintptr_t)255);
   const int n_blk = (int)((NR + kPackRows - 1) / kPackRows);
   int* rowmap = (int*)p;
@@ -995,9 +1007,11 @@ static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack
   int* bfr = (int*)p;
   p += up256((size_t)n_blk * sizeof(int));
   int* counts = (int*)p;
-  eodm_pack_count_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, bfr);
-  eodm_pack_scan_kernel<<<1, 1024, 0, st>>>(bsum, bfr, n_blk, counts);
-  eodm_pack_fill_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, rowmap, wflag);
+  if (packed_n == 0) {
+    eodm_pack_count_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, bfr);
+    eodm_pack_scan_kernel<<<1, 1024, 0, st>>>(bsum, bfr, n_blk, counts);
+    eodm_pack_fill_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, rowmap, wflag);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     eodm_set_error("row packing kernels failed to launch: %s", cudaGetErrorString(e));
@@ -1011,6 +1025,13 @@ static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack
 
 extern "C" void eodm_debug_set_packing(int on) { g_packing = on; }
 
+// Packs the rows of a batch once for several walks (the tables of a multi-order step, or the forward and the VJP of one
+// step): n = the largest kernel_size among them; the walks are then launched with packed_n = n.
+int eodm_pack_rows_launch(const uint8_t* mask, int B, int T, int n, void* pack_ws, cudaStream_t st) {
+  PackView pk;
+  return pack_rows(mask, (long long)B * T, T, n, pack_ws, st, &pk, 0);
+}
+
 // Which windows-per-lane variant to launch is decided on the host, but the number of packed rows is known on the device
 // only.  A caller that repeats similar batches (a session) passes a pinned host word: this launch copies its packed row
 // count there (asynchronously, on the stream) and plans with whatever an earlier launch left -- a stale hint costs
@@ -1023,12 +1044,12 @@ static long long plan_rows(long long NR, const PackView& pk, int* rows_host, cud
 }
 
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           float* W, void* ws, cudaStream_t st, void* pack_ws, int* rows_host) {
+                           float* W, void* ws, cudaStream_t st, void* pack_ws, int* rows_host, int packed_n) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   PackView pk;
   {
-    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
+    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk, packed_n);
     if (rc != EODM_OK) return rc;
   }
   if (!rows_host) rows_host = t->rows_host;   // no caller-side hint: the table's own
@@ -1085,12 +1106,13 @@ int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* 
 }
 
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
-                           float* dpx, void* ws, cudaStream_t st, int accumulate, void* pack_ws, int* rows_host) {
+                           float* dpx, void* ws, cudaStream_t st, int accumulate, void* pack_ws, int* rows_host,
+                           int packed_n) {
   const int n = t->n, V = t->V;
   const long long NR = (long long)B * T;
   PackView pk;
   {
-    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk);
+    const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk, packed_n);
     if (rc != EODM_OK) return rc;
     // rows outside every window are not visited any more: their gradient is zero
     if (pk.rowmap && !accumulate && cudaMemsetAsync(dpx, 0, sizeof(float) * (size_t)NR * V, st) != cudaSuccess) {

@@ -14,11 +14,13 @@ size_t eodm_counts_workspace_bytes(const eodm_table* t);
 // window, gathered through a row map built on the spot (ragged batches: the padding is skipped row by row, not tile by tile)
 size_t eodm_pack_workspace_bytes(long long NR);
 int eodm_counts_fwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, float* S, float* N,
-                           float* W, void* ws, cudaStream_t st, void* pack_ws = nullptr,
-                           int* rows_host = nullptr);   // W (optional): valid window starts; rows_host: see plan_rows
+                           float* W, void* ws, cudaStream_t st, void* pack_ws = nullptr, int* rows_host = nullptr,
+                           int packed_n = 0);   // W (optional): valid window starts; rows_host: see plan_rows
+// packs once for several walks of the same batch (n = their largest kernel_size); the walks then take packed_n = n
+int eodm_pack_rows_launch(const uint8_t* mask, int B, int T, int n, void* pack_ws, cudaStream_t st);
 int eodm_counts_bwd_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS,
                            float* dpx, void* ws, cudaStream_t st, int accumulate = 0, void* pack_ws = nullptr,
-                           int* rows_host = nullptr);   // accumulate: dpx += ...
+                           int* rows_host = nullptr, int packed_n = 0);   // accumulate: dpx += ...
 
 // tcfwd.cu -- tcgen05 forward for trigram-only tables over V <= 48
 bool eodm_tcf_supported(const eodm_table* t);
