@@ -331,19 +331,24 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       if (t128 == 0) a.partN[slice] = n_frames;
     }
   } else {
-    // ------------------------------------------------------------------ A producers: warpgroup g = M tile g, thread = pair row
-    const int g = warp >> 2, quarter = warp & 3, l128 = tid & 127;
+    // ------------------------------------------------------------------ A producers
+    // The CTA's 256 pairs are a 16 x 16 block of the (a, b) grid: M tile g holds a = A0 + 8 g + (row >> 4), b = B0 + (row & 15),
+    // so rows l of the two tiles share b.  A producer thread forms BOTH tiles' row l for a stage -- one px[w+1, b] operand,
+    // two px[w, a] operands: 12 LDS.128 per 32 products instead of 16 (the kernel is bound by the shared-memory data pipe,
+    // profiles/r02_tcfwd.md) -- and the two groups of four warps take the stages in turn (group h: stages c = h, h+2, ..).
+    // Group h also keeps the running sums of tile h: it adds the accumulators of a round after its first stage of the next.
+    const int h = warp >> 2, quarter = warp & 3, l128 = tid & 127;
     const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    const int pair = (mg * kMT + g) * 128 + l128;
-    const int pa = pair / kVP, pb = pair - pa * kVP;
+    const int A0 = (mg / 3) * 16, B0 = (mg % 3) * 16;
+    const int pb = B0 + (l128 & 15), pa0 = A0 + (l128 >> 4), pa1 = pa0 + 8;
     float acc[kVP];
 #pragma unroll
     for (int k = 0; k < kVP; ++k) acc[k] = 0.f;
 
-    auto drain = [&](int r) {   // add round r's accumulators (both halves of a row) into the register sums
-      mbar_wait(&bars.d_full[g], (uint32_t)(r & 1));
+    auto drain = [&](int r) {   // add round r's accumulators of tile h (both halves of a row) into the register sums
+      mbar_wait(&bars.d_full[h], (uint32_t)(r & 1));
       tc_fence_after();
-      const uint32_t d = tmem + lane_field + (uint32_t)(g * 96);
+      const uint32_t d = tmem + lane_field + (uint32_t)(h * 96);
 #pragma unroll
       for (int cg = 0; cg < kVP; cg += 16) {
         uint32_t v0[16], v1[16];
@@ -356,53 +361,67 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.d_empty[g]);
+      if (lane == 0) mbar_arrive(&bars.d_empty[h]);
     };
 
-    int i = 0;
     for (int k = 0; k < n_tiles; ++k) {
       const int buf = k & 1;
       mbar_wait(&bars.pt_full[buf], (uint32_t)((k >> 1) & 1));
-      const float* r0 = tile0 + (size_t)buf * kTileFloats + pa * kRSF;                 // px[w, a] + eps
-      const float* r1 = tile0 + (size_t)buf * kTileFloats + kPeFloats + pb * kRSF;     // px[w+1, b] + eps
+      const float* tb = tile0 + (size_t)buf * kTileFloats;
+      const float* rx0 = tb + pa0 * kRSF;                 // px[w, a] + eps, tile 0's a
+      const float* rx1 = tb + pa1 * kRSF;                 //                 tile 1's a
+      const float* ry = tb + kPeFloats + pb * kRSF;       // px[w+1, b] + eps
       const int nst = min(kStPerTile, total_st - k * kStPerTile);
-      // (Requesting the next stage's operands before the handshake and multiplying after it was tried: 0.31 ms against
-      // 0.24 ms -- the loads then sit in the same dependency window as the TMEM stores.  profiles/r02_tcfwd.md)
+      bool drained = k == 0;
 #pragma unroll 1
-      for (int c = 0; c < nst; ++c, ++i) {
+      for (int c = h; c < nst; c += 2) {
+        const int i = k * kStPerTile + c;
         const int s = i % kNA, use = i / kNA;
-        float q[16];
+        float4 y[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 x = *reinterpret_cast<const float4*>(r0 + c * kSt + 4 * u);
-          const float4 y = *reinterpret_cast<const float4*>(r1 + c * kSt + 4 * u);
-          q[4 * u] = x.x * y.x; q[4 * u + 1] = x.y * y.y; q[4 * u + 2] = x.z * y.z; q[4 * u + 3] = x.w * y.w;
-        }
-        uint32_t hi[16], lo[16];
+        for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(ry + c * kSt + 4 * u);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          hi[u] = __float_as_uint(q[u]);   // the tensor core reads the 19 upper bits
-          lo[u] = __float_as_uint(q[u] - __uint_as_float(hi[u] & 0xffffe000u));
+        for (int g = 0; g < kMT; ++g) {
+          const float* rx = g == 0 ? rx0 : rx1;
+          float q[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 x = *reinterpret_cast<const float4*>(rx + c * kSt + 4 * u);
+            q[4 * u] = x.x * y[u].x; q[4 * u + 1] = x.y * y[u].y; q[4 * u + 2] = x.z * y[u].z; q[4 * u + 3] = x.w * y[u].w;
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            hi[u] = __float_as_uint(q[u]);   // the tensor core reads the 19 upper bits
+            lo[u] = __float_as_uint(q[u] - __uint_as_float(hi[u] & 0xffffe000u));
+          }
+          if (use > 0) {
+            mbar_wait(&bars.a_free[g][s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage are done
+            tc_fence_after();
+          }
+          const uint32_t ab = tmem + lane_field + kColA + (uint32_t)((kMT * s + g) * 32);
+          tmem_st16(ab, hi);
+          tmem_st16(ab + 16u, lo);
         }
-        if (use > 0) {
-          mbar_wait(&bars.a_free[g][s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage are done
-          tc_fence_after();
-        }
-        const uint32_t ab = tmem + lane_field + kColA + (uint32_t)((kMT * s + g) * 32);
-        tmem_st16(ab, hi);
-        tmem_st16(ab + 16u, lo);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (elect_one_f()) mbar_arrive(&bars.a_full[g][s]);
-        // the previous round's accumulators, once this round's first stage is on its way
-        if (i > 0 && (i % kStPerTile) == 0) drain(i / kStPerTile - 1);
+        if (elect_one_f()) {
+          mbar_arrive(&bars.a_full[0][s]);
+          mbar_arrive(&bars.a_full[1][s]);
+        }
+        // the previous round's accumulators, once this round's first stage of the group is on its way
+        if (!drained) {
+          drain(k - 1);
+          drained = true;
+        }
       }
+      if (!drained) drain(k - 1);   // (a last round too short for this group to have a stage in)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.pt_free[buf]);
     }
-    if (i > 0) drain((i - 1) / kStPerTile);
-    float* out = a.partS + ((size_t)slice * (kMTiles * 128) + pair) * kVP;
+    if (n_tiles > 0) drain(n_tiles - 1);
+    float* out = a.partS + ((size_t)slice * (kMTiles * 128) + (size_t)((h == 0 ? pa0 : pa1) * kVP + pb)) * kVP;
 #pragma unroll
     for (int k = 0; k < kVP; k += 4)
       *reinterpret_cast<float4*>(out + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
