@@ -19,7 +19,9 @@
 //     in divergent code needs ~130 dependent instructions per K-step and sets the pace (profiles/r02_tcbwd.md);
 //   * stages of 16 windows (two K-steps), so barrier traffic per MMA is halved.
 //
-// A CTA owns MT = 2 M tiles and a slice of the batch; CTAs are arranged as (9 tile groups) x (sm_count / 9 slices).  The
+// A CTA owns MT = 2 M tiles -- a 16 x 16 block of the (a, b) grid, so that rows l of the two tiles share b and one producer
+// thread forms both from one px[w+1, b] operand -- and a slice of the batch; CTAs are arranged as (9 blocks) x (sm_count / 9
+// slices).  The
 // accumulators live in TMEM for one round of 128 windows (32 accumulations per element: the tensor core adds with
 // truncation, -3.7e-8 relative per MMA) and are then added, round to nearest, to fp32 sums in the producer threads'
 // registers (one accumulator bank: the TMEM columns go to five A stages per tile instead, which the producer -> issuer ->
@@ -29,7 +31,7 @@
 // out of the staged tile with no per-stage work.  At the end every CTA writes its sums to a per-slice partial and a
 // second kernel gathers the K table entries and adds the slices in a fixed order: deterministic, no float atomics.
 //
-// Status (profiles/r02_tcfwd.md): 0.173 ms at timit_c2 against 0.252 ms for the trie walk.  The MMAs would take 0.08 ms;
+// Status (profiles/r02_tcfwd.md): 0.160 ms at timit_c2 against 0.252 ms for the trie walk.  The MMAs would take 0.08 ms;
 // the kernel is bound by the shared-memory data pipe (83 % busy: two words loaded per product formed, the B tile read by
 // the tensor core, the staging stores) -- the generated operand, 2304 x W products split into hi and remainder, is the
 // cost of putting a Khatri-Rao contraction on a GEMM unit.
@@ -58,7 +60,7 @@ constexpr int kNA = 5;                  // A stages per M tile (TMEM columns 192
 constexpr int kBChunk = 96 * 4 + 4;     // floats per 4-window chunk of the B tile: [96 rows][4] + one 16-byte pad, so that
                                         // the staging stores of 32 consecutive rows fall into 32 banks
 constexpr int kBFloats = (kTile / 4) * kBChunk;
-constexpr int kThreadsF = 448;          // warps 0-7 producers (tile g = warp / 4), 8-11 staging, 12-13 MMA issue
+constexpr int kThreadsF = 448;          // warps 0-7 producers (stages in turn: group warp / 4), 8-11 staging, 12-13 MMA issue
 constexpr float kEpsF = 1e-15f;
 constexpr int kPeFloats = kPeRows * kRSF;
 constexpr int kRawFloats = 130 * kVP;    // one raw posterior tile [130 rows][V] as it lies in global memory (bulk copy)
