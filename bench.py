@@ -360,17 +360,17 @@ def main():
     lds_peak = 0.90 * n_sm * sm_max * 1e6
     if E.uses_tensor_fwd(table):
         # the tensor-core forward is bound by the shared-memory data pipe (profiles/r02_tcfwd.md): per 128-window tile and
-        # CTA (9 groups of 256 pairs) the producers' operand loads (8 warps x 8 stages x 8 LDS.128 x 4 wavefronts), the
+        # CTA (9 blocks of 256 pairs) the producers' operand loads (8 warps x 4 stages each x 12 LDS.128 x 4 wavefronts), the
         # tensor core's reads of the B tile (16 K-steps x 2 M tiles x (96 + 48) rows x 32 B / 128 B), the staging stores
         # (Pe0, Pe1, B hi / remainder: 3 x 48 KB / 128 B... measured 870 with the padding) and the staging loads (288)
         tiles = (B * T + 127) // 128 * 9
-        wf_tc = float(tiles) * (2048 + 1152 + 870 + 288)
+        wf_tc = float(tiles) * (1536 + 1152 + 870 + 288)
         pipe_peak = 1.0 * n_sm * sm_max * 1e6
         roofline["smem_pipe"] = {
             "fwd": {"wavefronts": wf_tc, "floor_ms": wf_tc / pipe_peak * 1e3, "frac": wf_tc / pipe_peak / t_f},
             "peak_wavefronts_per_clk_per_sm": 1.0,
             "note": "128-byte wavefronts of the shared-memory data pipe (LSU + tensor-core operand reads); ncu measures "
-                    "34.6 M per launch at timit_c2 (profiles/r02_tc_ncu.txt); the resource that binds the tensor-core forward"}
+                    "29.5 M per launch at timit_c2 (profiles/r02_tc_ncu.txt); the resource that binds the tensor-core forward"}
     roofline["smem_wavefronts"] = {
         "fwd": {"algorithmic": wf_f, "floor_ms": wf_f / lds_peak * 1e3, "frac": wf_f / lds_peak / t_f},
         "peak_wavefronts_per_clk_per_sm": 0.90, "note": "measured LDS.32 rate; the resource that binds the trie walk"}
