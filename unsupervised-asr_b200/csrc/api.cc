@@ -299,10 +299,10 @@ struct eodm_session {
   const eodm_table* t;
   int maxB, maxT, device;
   cudaStream_t st, copy_st;       // compute stream, copy stream of the pipelined host-buffer step
-  cudaEvent_t ev_in[2], ev_out[2], ev_done;
+  cudaEvent_t ev_in[3], ev_out[3], ev_done;
   float *logits, *px, *dpx, *dlogits;
   float* counts;   // [K + 1]: S then N (packed for one all-reduce)
-  float* counts2;  // [2][K + 1]: per-chunk partial counts of the pipelined step
+  float* counts2;  // [3][K + 1]: per-chunk partial counts of the pipelined step
   float *py, *gS, *loss;
   uint8_t* mask;
   void* ws;
@@ -313,7 +313,7 @@ struct eodm_session {
   struct Slot {
     float *logits, *dlogits, *loss;
     uint8_t* mask;
-    cudaEvent_t in[2], out[2], loss_ready, done;
+    cudaEvent_t in[3], out[3], loss_ready, done;
     bool busy;
   } slot[2];
   cudaStream_t h2d_st, d2h_st;
@@ -329,12 +329,12 @@ static void session_free(eodm_session* s) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (s->rows_host) cudaFreeHost(s->rows_host);
-  for (cudaEvent_t ev : {s->ev_in[0], s->ev_in[1], s->ev_out[0], s->ev_out[1], s->ev_done})
+  for (cudaEvent_t ev : {s->ev_in[0], s->ev_in[1], s->ev_in[2], s->ev_out[0], s->ev_out[1], s->ev_out[2], s->ev_done})
     if (ev) cudaEventDestroy(ev);
   for (auto& sl : s->slot) {
     for (void* p : {(void*)sl.logits, (void*)sl.dlogits, (void*)sl.loss, (void*)sl.mask})
       if (p) cudaFree(p);
-    for (cudaEvent_t ev : {sl.in[0], sl.in[1], sl.out[0], sl.out[1], sl.loss_ready, sl.done})
+    for (cudaEvent_t ev : {sl.in[0], sl.in[1], sl.in[2], sl.out[0], sl.out[1], sl.out[2], sl.loss_ready, sl.done})
       if (ev) cudaEventDestroy(ev);
   }
   if (s->h2d_st) cudaStreamDestroy(s->h2d_st);
@@ -363,7 +363,7 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   cudaError_t e = cudaSetDevice(t->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking);
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
   }
@@ -374,7 +374,7 @@ extern "C" int eodm_session_create(const eodm_table* t, const float* py_host, in
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->dlogits, el);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->mask, rows);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts, ((size_t)t->K + 1) * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts2, 2 * ((size_t)t->K + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts2, 3 * ((size_t)t->K + 1) * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->py, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->gS, (size_t)t->K * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->loss, 256);
@@ -468,19 +468,42 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   return rc;
 }
 
-// Two halves of the batch, pipelined over a copy stream and the compute stream:
-//   H2D(0) H2D(1)                      |            D2H(0)      D2H(1)
-//          softmax+counts(0) softmax+counts(1) -> sum -> [allreduce] -> loss -> VJP(0) VJP(1)
-// Each half keeps a whole number of tiles per SM, so the kernels run as efficiently as on the full batch.
+// How a host-buffer step is cut into chunks of utterances (the same rule for the synchronous call and for submit, so that
+// both add the chunks' partial counts in the same order): thirds from 6 MiB of logits, halves from 2 MiB, else one piece.
+// Thirds of the bench batch keep the tensor-core VJP at six rounds of tile pairs in total, as halves and the whole batch do.
+static int session_chunks(int B, int T, int V, int Bc[3], size_t row0[3]) {
+  const size_t bytes = (size_t)B * T * V * sizeof(float);
+  const int nch = (B >= 3 && bytes >= ((size_t)6 << 20)) ? 3 : (B >= 2 && bytes >= ((size_t)2 << 20)) ? 2 : 1;
+  int b0 = 0;
+  for (int c = 0; c < 3; ++c) {
+    Bc[c] = c < nch ? (c + 1 < nch ? B / nch : B - b0) : 0;
+    row0[c] = (size_t)b0 * T;
+    b0 += Bc[c];
+  }
+  return nch;
+}
+// the chunks' packed [S, N] vectors added in chunk order into s->counts
+static int session_add_chunks(eodm_session* s, int nch) {
+  const int K1 = s->t->K + 1;
+  int rc = eodm_add_vectors_launch(s->counts2, s->counts2 + K1, K1, s->counts, s->st);
+  for (int c = 2; c < nch && rc == EODM_OK; ++c)
+    rc = eodm_add_vectors_launch(s->counts, s->counts2 + (size_t)c * K1, K1, s->counts, s->st);
+  return rc;
+}
+
+// Chunks of the batch, pipelined over a copy stream and the compute stream:
+//   H2D(0) H2D(1) H2D(2)                                   |         D2H(0)   D2H(1)   D2H(2)
+//          fwd(0)  fwd(1)  fwd(2) -> sum -> [allreduce] -> loss -> VJP(0)   VJP(1)   VJP(2)       (fwd = softmax + counts)
 static int session_loss_pipelined(eodm_session* s, const float* logits_host, const uint8_t* mask_host, int B, int T,
                                   void* comm, float* loss_host, float* dlogits_host) {
   const eodm_table* t = s->t;
   const int V = t->V, K = t->K;
-  const int Bc[2] = {B / 2, B - B / 2};
-  size_t row0[2] = {0, (size_t)Bc[0] * T};
+  int Bc[3];
+  size_t row0[3];
+  const int nch = session_chunks(B, T, V, Bc, row0);
   int rc = EODM_OK;
   cudaError_t e = cudaSuccess;
-  for (int c = 0; c < 2 && e == cudaSuccess; ++c) {
+  for (int c = 0; c < nch && e == cudaSuccess; ++c) {
     const size_t rows = (size_t)Bc[c] * T;
     e = cudaMemcpyAsync(s->logits + row0[c] * V, logits_host + row0[c] * V, rows * V * sizeof(float),
                         cudaMemcpyHostToDevice, s->copy_st);
@@ -488,14 +511,14 @@ static int session_loss_pipelined(eodm_session* s, const float* logits_host, con
       e = cudaMemcpyAsync(s->mask + row0[c], mask_host + row0[c], rows, cudaMemcpyHostToDevice, s->copy_st);
     if (e == cudaSuccess) e = cudaEventRecord(s->ev_in[c], s->copy_st);
   }
-  for (int c = 0; c < 2 && e == cudaSuccess && rc == EODM_OK; ++c) {
+  for (int c = 0; c < nch && e == cudaSuccess && rc == EODM_OK; ++c) {
     e = cudaStreamWaitEvent(s->st, s->ev_in[c], 0);
     if (e != cudaSuccess) break;
     float* cc = s->counts2 + (size_t)c * (K + 1);
     rc = eodm_softmax_fwd_launch(s->logits + row0[c] * V, (int64_t)Bc[c] * T, V, s->px + row0[c] * V, s->st);
     if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
   }
-  if (e == cudaSuccess && rc == EODM_OK) rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  if (e == cudaSuccess && rc == EODM_OK) rc = session_add_chunks(s, nch);
   bool image_ready = false;
   if (e == cudaSuccess && rc == EODM_OK)
     rc = session_exchange_and_loss(s, s->counts, comm, s->loss, dlogits_host != nullptr, s->st, &image_ready);
@@ -503,7 +526,7 @@ static int session_loss_pipelined(eodm_session* s, const float* logits_host, con
   if (e == cudaSuccess && rc == EODM_OK) e = cudaStreamWaitEvent(s->copy_st, s->ev_done, 0);
   if (e == cudaSuccess && rc == EODM_OK)
     e = cudaMemcpyAsync(loss_host, s->loss, sizeof(float), cudaMemcpyDeviceToHost, s->copy_st);
-  for (int c = 0; c < 2 && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
+  for (int c = 0; c < nch && dlogits_host && e == cudaSuccess && rc == EODM_OK; ++c) {
     const size_t rows = (size_t)Bc[c] * T;
     rc = session_vjp(s, s->px + row0[c] * V, s->mask + row0[c], Bc[c], T, s->dpx + row0[c] * V, s->st, image_ready);
     if (rc == EODM_OK)
@@ -536,8 +559,13 @@ extern "C" int eodm_session_loss(eodm_session* s, const float* logits_host, cons
   DeviceGuard guard(s->device);
   CUDA_TRY(guard.err);
   const size_t rows = (size_t)B * T, el = rows * s->t->V * sizeof(float);
-  // copies worth overlapping (>= 2 MiB each way) and two non-empty halves
-  if (B >= 2 && el >= ((size_t)2 << 20)) return session_loss_pipelined(s, logits_host, mask_host, B, T, comm, loss_host, dlogits_host);
+  // copies worth overlapping: the batch goes through in chunks (session_chunks)
+  {
+    int Bc[3];
+    size_t row0[3];
+    if (session_chunks(B, T, s->t->V, Bc, row0) >= 2)
+      return session_loss_pipelined(s, logits_host, mask_host, B, T, comm, loss_host, dlogits_host);
+  }
   int rc = EODM_OK;
   cudaError_t e = cudaMemcpyAsync(s->logits, logits_host, el, cudaMemcpyHostToDevice, s->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->mask, mask_host, rows, cudaMemcpyHostToDevice, s->st);
@@ -572,7 +600,7 @@ static int session_slots_init(eodm_session* s) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&sl.dlogits, el);
     if (e == cudaSuccess) e = cudaMalloc((void**)&sl.mask, rows);
     if (e == cudaSuccess) e = cudaMalloc((void**)&sl.loss, 256);
-    for (cudaEvent_t* ev : {&sl.in[0], &sl.in[1], &sl.out[0], &sl.out[1], &sl.loss_ready, &sl.done})
+    for (cudaEvent_t* ev : {&sl.in[0], &sl.in[1], &sl.in[2], &sl.out[0], &sl.out[1], &sl.out[2], &sl.loss_ready, &sl.done})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
@@ -597,9 +625,9 @@ extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logit
   REQUIRE(!sl.busy, EODM_EINVAL, "slot %d is still in flight: call eodm_session_wait first", slot);
   const eodm_table* t = s->t;
   const int V = t->V, K = t->K;
-  const int nch = (B >= 2 && (size_t)B * T * V * sizeof(float) >= ((size_t)2 << 20)) ? 2 : 1;
-  const int Bc[2] = {nch == 2 ? B / 2 : B, B - B / 2};
-  const size_t row0[2] = {0, (size_t)Bc[0] * T};
+  int Bc[3];
+  size_t row0[3];
+  const int nch = session_chunks(B, T, V, Bc, row0);
   cudaError_t e = cudaSuccess;
   for (int c = 0; c < nch && e == cudaSuccess; ++c) {
     const size_t rows = (size_t)Bc[c] * T;
@@ -611,12 +639,11 @@ extern "C" int eodm_session_submit(eodm_session* s, int slot, const float* logit
   for (int c = 0; c < nch && e == cudaSuccess && rc == EODM_OK; ++c) {
     e = cudaStreamWaitEvent(s->st, sl.in[c], 0);
     if (e != cudaSuccess) break;
-    float* cc = nch == 2 ? s->counts2 + (size_t)c * (K + 1) : s->counts;
+    float* cc = nch >= 2 ? s->counts2 + (size_t)c * (K + 1) : s->counts;
     rc = eodm_softmax_fwd_launch(sl.logits + row0[c] * V, (int64_t)Bc[c] * T, V, s->px + row0[c] * V, s->st);
     if (rc == EODM_OK) rc = eodm_counts_fwd(t, s->px + row0[c] * V, sl.mask + row0[c], Bc[c], T, cc, cc + K, s->ws, s->st);
   }
-  if (e == cudaSuccess && rc == EODM_OK && nch == 2)
-    rc = eodm_add_vectors_launch(s->counts2, s->counts2 + (K + 1), K + 1, s->counts, s->st);
+  if (e == cudaSuccess && rc == EODM_OK && nch >= 2) rc = session_add_chunks(s, nch);
   bool image_ready = false;
   if (e == cudaSuccess && rc == EODM_OK)
     rc = session_exchange_and_loss(s, s->counts, comm, sl.loss, dlogits_host != nullptr, s->st, &image_ready);
