@@ -38,6 +38,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/eodm_b200.h"
 #include "kernels.h"
 #include "table.h"
@@ -249,10 +251,15 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
       // (issued below, right after the previous tile's pass), and the loads are shared-memory loads.  Loading the rows
       // straight from global memory instead (16 bytes per lane, 768 bytes apart) fills the SM's miss queue with 2300
       // sectors per tile and left the staging 6-7 thousand clocks behind the MMAs (profiles/r02_tcfwd.md).
+      // The staging warps issue ~800 instructions per tile and share their schedulers with the producers: they, not the
+      // barriers, set the tile period (profiles/r02_tcfwd.md).  FAST = the common tile: all 130 rows inside the batch and
+      // V = 48, so none of the bounds selects is needed.
+      auto stage_body = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
       float4 ld[3][6];
       bool inr[6];
 #pragma unroll
-      for (int rr = 0; rr < 6; ++rr) inr[rr] = st0 + 4 * lane + rr < a.NR;
+      for (int rr = 0; rr < 6; ++rr) inr[rr] = FAST || st0 + 4 * lane + rr < a.NR;
       if (a.bulk) {
         mbar_wait(&bars.raw_full, (uint32_t)(k & 1));
 #pragma unroll
@@ -260,9 +267,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
 #pragma unroll
           for (int rr = 0; rr < 6; ++rr) {
             const int r = 4 * lane + rr;
-            ld[it][rr] = (r < 130 && inr[rr]) ? *reinterpret_cast<const float4*>(raw + r * V + 4 * qof(it))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * qof(it) >= V) ld[it][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FAST) {
+              ld[it][rr] = *reinterpret_cast<const float4*>(raw + r * kVP + 4 * qof(it));
+            } else {
+              ld[it][rr] = (r < 130 && inr[rr]) ? *reinterpret_cast<const float4*>(raw + r * V + 4 * qof(it))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * qof(it) >= V) ld[it][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
       } else {
 #pragma unroll
@@ -299,10 +310,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
           const bool in = inr[rr];
-          rows[rr][0] = (in && 4 * q < V) ? ld[it][rr].x + kEpsF : 0.f;
-          rows[rr][1] = (in && 4 * q + 1 < V) ? ld[it][rr].y + kEpsF : 0.f;
-          rows[rr][2] = (in && 4 * q + 2 < V) ? ld[it][rr].z + kEpsF : 0.f;
-          rows[rr][3] = (in && 4 * q + 3 < V) ? ld[it][rr].w + kEpsF : 0.f;
+          rows[rr][0] = (FAST || (in && 4 * q < V)) ? ld[it][rr].x + kEpsF : 0.f;
+          rows[rr][1] = (FAST || (in && 4 * q + 1 < V)) ? ld[it][rr].y + kEpsF : 0.f;
+          rows[rr][2] = (FAST || (in && 4 * q + 2 < V)) ? ld[it][rr].z + kEpsF : 0.f;
+          rows[rr][3] = (FAST || (in && 4 * q + 3 < V)) ? ld[it][rr].w + kEpsF : 0.f;
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -320,6 +331,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
           *reinterpret_cast<float4*>(bo + 48 * 4) = make_float4(l[0], l[1], l[2], l[3]);
         }
       }
+      };
+      if (a.bulk && V == kVP && st0 + 130 <= a.NR) stage_body(std::true_type{});
+      else stage_body(std::false_type{});
       fence_async_smem();   // the B tile is read by the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.pt_full[buf]);
