@@ -719,6 +719,54 @@ def test_fused_tail_and_peer_tail_on_one_gpu(eodm):
         s_.close()
 
 
+@pytest.mark.parametrize("V,n,K,B,T,mixed", [(40, 5, 1000, 24, 70, False), (48, 3, 3000, 9, 200, True), (72, 4, 2048, 12, 96, False),
+                                             (20, 2, 150, 7, 33, False)])
+def test_row_packing_with_arbitrary_masks(eodm, V, n, K, B, T, mixed):
+    """The walk over packed rows (counts.cu: only the rows that take part in a valid window are visited, gathered and
+    scattered through a row map) against the walk over the padded rows and against the oracle -- for masks that are NOT
+    prefixes: holes inside utterances, valid frames in the last n-1 slots, empty utterances, and one all-valid batch.
+    The reference tests only the window START (models/EODM.py:19), so a window may run over masked frames."""
+    from eodm_b200._lib import lib
+    dev = _dev()
+    rng = np.random.default_rng(V * n + T)
+    ids, py, _, _ = _random_case(V + n, V, n, K, 3, T, mixed)      # the table only (mixed: orders 0..n in one table)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    masks = []
+    m = rng.random((B, T)) < 0.6                       # holes everywhere
+    m[0] = False                                       # an empty utterance
+    m[1] = True                                        # a full one
+    m[2, :] = False; m[2, T - 1] = True                # a valid frame no window can start at (it still counts in N)
+    m[3, :] = False; m[3, T - n] = True                # the last possible window start
+    masks.append(m)
+    lens = rng.integers(n, T + 1, size=B)
+    masks.append(np.arange(T)[None, :] < lens[:, None])   # ordinary ragged prefixes
+    masks.append(np.ones((B, T), dtype=bool))
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    px = eodm.softmax_fwd(torch.tensor(logits, device=dev))
+    px64 = px.cpu().numpy().astype(np.float64)
+    gS = torch.tensor(rng.standard_normal(K).astype(np.float32), device=dev)
+    try:
+        lib.eodm_debug_set_path(1)                     # the walk, whatever the table
+        for mask in masks:
+            mt = torch.tensor(mask, device=dev)
+            out = {}
+            for packing in (1, 0):
+                lib.eodm_debug_set_packing(packing)
+                out[packing] = (eodm.counts_fwd(table, px, mt).cpu().numpy(), eodm.counts_bwd(table, px, mt, gS).cpu().numpy())
+            S_ref, N_ref = O.counts_fwd(px64, mask, ids, n)
+            d_ref = O.counts_bwd(px64, mask, ids, n, gS.cpu().numpy().astype(np.float64))
+            for packing in (1, 0):
+                c, d = out[packing]
+                assert c[K] == N_ref
+                assert np.abs(c[:K] - S_ref).max() <= TOL * max(np.abs(S_ref).max(), 1e-30)
+                assert rel_max(d, d_ref) <= TOL
+            # rows outside every window: exactly zero on both paths
+            assert np.array_equal(out[1][1] == 0, out[0][1] == 0) or rel_max(out[1][1], out[0][1]) <= TOL
+    finally:
+        lib.eodm_debug_set_packing(1)
+        lib.eodm_debug_set_path(0)
+
+
 def test_legacy_partial_sums(eodm):
     """SURVEY 8a row a6 -- models/EODM.py:28-52: un-normalised (pz, K) per device, K = the mask cut to the window
     starts; two "devices" (halves of the batch) summed on the host and divided as main_es.py:331-335 does."""

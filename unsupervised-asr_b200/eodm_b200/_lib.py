@@ -100,6 +100,7 @@ _DEBUG_SIGNATURES = {
     "eodm_table_debug_trie": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "eodm_debug_set_tiling": (None, [_i, _i]),
     "eodm_debug_set_path": (None, [_i]),
+    "eodm_debug_set_packing": (None, [_i]),
     "eodm_debug_tcb_profile": (None, [_p]),
     "eodm_debug_tcb_switches": (None, [_i]),
 }
