@@ -71,9 +71,9 @@ static int fwd_path(const eodm_table* t) {
   if (g_path == 1) return 0;
   if (g_path == 2) return eodm_tcf_supported(t) ? 3 : 0;
   if (!eodm_tcf_supported(t)) return 0;
-  // measured at timit_c2 (profiles/r02_tcfwd.md): the tensor-core forward costs ~500 SM-clocks per row whatever the table
+  // measured at timit_c2 (profiles/r02_tcfwd.md): the tensor-core forward costs ~450 SM-clocks per row whatever the table
   // holds (it is bound by forming the 2304 x W operand, not by the MMAs); the walk costs ~0.057 per trie node and row.
-  const double tc_clk_per_row = 500.0, walk_clk_per_row = 0.0567 * (double)t->trie[0].n_nodes;
+  const double tc_clk_per_row = 450.0, walk_clk_per_row = 0.0567 * (double)t->trie[0].n_nodes;
   return tc_clk_per_row < walk_clk_per_row ? 3 : 0;
 }
 
