@@ -799,7 +799,9 @@ def test_session_submit_wait_matches_synchronous_call(eodm):
     interleaving, for batches large enough to take the two-half pipeline and for small ones."""
     from eodm_b200.session import PinnedArray
     dev = _dev()
-    for (V, n, K, B, T) in [(48, 3, 3000, 64, 400), (40, 5, 500, 3, 30)]:
+    from oracle import fast as F
+    # (48, 3, 10000, 100, 400): 7.7 MB of logits -- three chunks, both counts kernels on the tensor cores
+    for (V, n, K, B, T) in [(48, 3, 3000, 64, 400), (40, 5, 500, 3, 30), (48, 3, 10000, 100, 400)]:
         ids, py = O.synth_table(V, n, K, seed=11)
         table = eodm.NgramTable.from_ids(ids, V, device=0)
         sess = eodm.Session(table, py, B, T)
@@ -821,6 +823,11 @@ def test_session_submit_wait_matches_synchronous_call(eodm):
         sess.wait(0)
         for (l_ref, d_ref), (lg, mk, dl, ls) in zip(ref, batches):
             assert float(ls.array[0]) == l_ref and np.array_equal(dl.array, d_ref)
+        # and the chunked host-buffer step against the oracle (first batch)
+        lg, mk, dl, ls = batches[0]
+        r = F.eodm_loss_direct(lg.array, mk.array.astype(bool), ids, n, py)
+        assert abs(float(ls.array[0]) - r["loss"]) <= TOL * abs(r["loss"])
+        assert rel_max(dl.array, r["dlogits"]) <= TOL
         with pytest.raises(eodm.EodmError):
             sess.wait(1)                                          # nothing in flight
         sess.close()
