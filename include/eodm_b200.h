@@ -201,6 +201,12 @@ void eodm_session_destroy(eodm_session* s);
 void* eodm_session_stream(eodm_session* s);
 /* Use a peer group (above) instead of the `comm` argument for the exchange of the following steps; NULL to undo. */
 int eodm_session_set_peer(eodm_session* s, eodm_peer* peer);
+/* Ragged batches on the tensor-core kernels (trigram tables over V <= 48): with packing on, eodm_session_step_device lists
+ * the rows that take part in a valid window, computes the softmax straight into that packed order, runs both counts kernels
+ * on the packed rows and scatters the gradient back -- the padding costs nothing instead of its full share of both kernels,
+ * for ~20 us of listing per step (worth it from ~10 % padding).  Tables that run the trie walk pack by themselves, always.
+ * Results agree with the padded path to rounding (other partial-sum boundaries).  Default: off. */
+int eodm_session_set_packing(eodm_session* s, int on);
 /* The same step on DEVICE buffers the caller already holds (a TF custom op, a CUDA graph):
  * softmax -> counts -> [allreduce] -> loss -> counts VJP -> softmax VJP, enqueued on `stream`
  * with the session's scratch; no copies, no synchronisation.  loss f32[1], dlogits

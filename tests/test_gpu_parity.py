@@ -767,6 +767,52 @@ def test_row_packing_with_arbitrary_masks(eodm, V, n, K, B, T, mixed):
         lib.eodm_debug_set_path(0)
 
 
+@pytest.mark.parametrize("V,K,B,T", [(48, 3000, 9, 200), (40, 2000, 30, 74), (47, 1500, 5, 131)])
+def test_session_packing_on_tensor_core_path(eodm, V, K, B, T):
+    """eodm_session_set_packing: the fused tensor-core step on physically packed rows (listing, softmax into packed order,
+    both counts kernels and the tail on the packed sequence, gradient scattered back) against the padded step and the
+    oracle -- ragged prefixes (the reference's shape: L = 74 slots, ~half of them used), masks with holes, all-valid."""
+    from eodm_b200._lib import lib
+    dev = _dev()
+    rng = np.random.default_rng(V + T)
+    ids, py = O.synth_table(V, 3, K, seed=V)
+    ids[K - 1] = ids[5]
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    lens = rng.integers(3, T + 1, size=B)
+    masks = [np.arange(T)[None, :] < lens[:, None], rng.random((B, T)) < 0.5, np.ones((B, T), dtype=bool)]
+    masks[1][0] = False
+    masks[1][1, :] = False; masks[1][1, T - 1] = True
+    table = eodm.NgramTable.from_ids(ids, V, device=0)
+    lg = torch.tensor(logits, device=dev)
+    st = torch.cuda.current_stream()
+    try:
+        lib.eodm_debug_set_path(2)                     # both counts kernels on the tensor cores, whatever the table
+        sess = eodm.Session(table, py, B, T)
+        for mask in masks:
+            m = torch.tensor(mask.astype(np.uint8), device=dev)
+            out = {}
+            for packing in (True, False, True):
+                sess.set_packing(packing)
+                loss, dl = torch.zeros(1, device=dev), torch.full_like(lg, 7.0)
+                sess.step_device(lg.data_ptr(), m.data_ptr(), B, T, loss.data_ptr(), dl.data_ptr(), st.cuda_stream)
+                torch.cuda.synchronize()
+                if packing and packing in out:
+                    assert torch.equal(out[True][0], loss) and torch.equal(out[True][1], dl)     # bit-reproducible
+                out[packing] = (loss, dl)
+            r = O.eodm_loss_direct(logits, mask, ids, 3, py)
+            for packing in (True, False):
+                loss, dl = out[packing]
+                assert abs(float(loss) - r["loss"]) <= TOL * abs(r["loss"]), (packing, float(loss), r["loss"])
+                assert rel_max(dl.cpu().numpy(), r["dlogits"]) <= TOL, packing
+            # rows outside every window: exactly zero on the packed path
+            assert float(out[True][1][~torch.tensor(np.logical_or.reduce([np.roll(mask, k, axis=1) & (np.arange(T)[None, :] >= k)
+                                                                         for k in range(3)]), device=dev)].abs().max()) == 0.0 \
+                if (~np.logical_or.reduce([np.roll(mask, k, axis=1) & (np.arange(T)[None, :] >= k) for k in range(3)])).any() else True
+        sess.close()
+    finally:
+        lib.eodm_debug_set_path(0)
+
+
 def test_legacy_partial_sums(eodm):
     """SURVEY 8a row a6 -- models/EODM.py:28-52: un-normalised (pz, K) per device, K = the mask cut to the window
     starts; two "devices" (halves of the batch) summed on the host and divided as main_es.py:331-335 does."""

@@ -308,6 +308,7 @@ struct eodm_session {
   void* ws;
   eodm_peer* peer;   // when set: the exchange + loss run as one kernel over peer memory (peer.cu)
   int* rows_host;    // pinned: packed row count of the previous batches (plan_rows in counts.cu)
+  int packing;       // eodm_session_set_packing: the fused tensor-core step works on physically packed rows
   // submit/wait (two steps in flight): per-slot input / output buffers and events, allocated at the first submit;
   // px, dpx, counts, gS and the workspace are shared -- they are only touched on the in-order compute stream
   struct Slot {
@@ -403,6 +404,12 @@ extern "C" int eodm_session_set_peer(eodm_session* s, eodm_peer* peer) {
   return EODM_OK;
 }
 
+extern "C" int eodm_session_set_packing(eodm_session* s, int on) {
+  REQUIRE(s, EODM_EINVAL, "null pointer");
+  s->packing = on ? 1 : 0;
+  return EODM_OK;
+}
+
 // exchange (if any) + loss + dloss/dS from this rank's packed counts
 static void* session_tcb_ws(const eodm_session* s) { return (char*)s->ws + counts_ws_aligned(s->t); }
 static void* session_tcf_ws(const eodm_session* s) { return (char*)session_tcb_ws(s) + tcb_ws_aligned(s->t); }
@@ -446,14 +453,32 @@ extern "C" int eodm_session_step_device(eodm_session* s, const float* logits, co
   const int64_t rows = (int64_t)B * T;
   float* S = s->counts;
   float* N = s->counts + t->K;
-  int rc = eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);
   bool image_ready = false;
   const EodmPeerView* pv = s->peer ? eodm_peer_view(s->peer) : nullptr;
-  if (rc == EODM_OK && dlogits && (s->peer ? pv != nullptr : !comm) && fwd_path(t) == 3 && use_tensor_bwd(t)) {
+  const bool fused = dlogits && (s->peer ? pv != nullptr : !comm) && fwd_path(t) == 3 && use_tensor_bwd(t);
+  const bool packed = fused && s->packing && rows <= 0x7fffffffLL;
+  int rc = packed ? EODM_OK : eodm_softmax_fwd_launch(logits, rows, t->V, s->px, st);   // (packed: the softmax follows the listing)
+  if (rc == EODM_OK && fused) {
     // both counts kernels on the tensor cores: what lies between them -- the forward's slice sums, the exchange over peer
     // memory when the session has a peer group, the loss, dloss/dS, the VJP's G image -- is one launch
     EodmTcfParts parts;
     rc = check_batch(t, s->px, mask, B, T);
+    if (rc == EODM_OK && packed) {
+      // Packed rows (eodm_session_set_packing): the step's five launches on the rows that take part in a window only.
+      // In the packed index space the batch is ONE sequence of *counts[0] rows with a window-start flag per row; the
+      // kernels read that count on the device.
+      EodmPackViews pk;
+      rc = eodm_pack_views_launch(mask, B, T, t->n, pack_ws_of(t, s->ws), st, &pk);
+      if (rc == EODM_OK) rc = eodm_softmax_fwd_packed_launch(logits, rows, t->V, pk.rowmap, pk.counts, s->px, st);
+      if (rc == EODM_OK) rc = eodm_tcf_launch_main(t, s->px, pk.wstart, 1, (int)rows, session_tcf_ws(s), st, &parts, pk.counts);
+      if (rc == EODM_OK)
+        rc = pv ? eodm_tc_tail_peer_launch(t, &parts, pv, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st, pk.counts + 1)
+                : eodm_tc_tail_launch(t, &parts, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st, pk.counts + 1);
+      if (rc == EODM_OK)
+        rc = eodm_tcb_launch(t, s->px, pk.wstart, 1, (int)rows, s->gS, s->dpx, session_tcb_ws(s), st, 0, 1, pk.counts);
+      if (rc == EODM_OK) rc = eodm_softmax_bwd_packed_launch(s->px, s->dpx, rows, t->V, pk.inv, dlogits, st);
+      return rc;
+    }
     if (rc == EODM_OK) rc = eodm_tcf_launch_main(t, s->px, mask, B, T, session_tcf_ws(s), st, &parts);
     if (rc == EODM_OK)
       rc = pv ? eodm_tc_tail_peer_launch(t, &parts, pv, S, N, s->py, 1e-15f, loss, s->gS, session_tcb_ws(s), st)

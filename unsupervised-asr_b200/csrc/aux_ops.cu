@@ -285,13 +285,15 @@ __global__ void __launch_bounds__(256) gather_softmax_fwd_vec_kernel(const float
 // plain softmax over rows (models/EODM.py:15) in the same 4-lane layout: NV independent 16-byte loads per thread
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __restrict__ x, int V, int64_t rows,
-                                                               float* __restrict__ y) {
+                                                               float* __restrict__ y, const int* __restrict__ rowmap = nullptr,
+                                                               const int* __restrict__ nrp = nullptr) {
   const unsigned gm = group_mask();
   const int gl = threadIdx.x & 3, V4 = V >> 2;
   const int64_t stride = (int64_t)gridDim.x * (blockDim.x / kG);
+  if (nrp) rows = *nrp;   // packed rows (sessions): row p is the softmax of padded row rowmap[p]
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / kG) + (threadIdx.x >> 2); row < rows; row += stride) {
     float4 r[NV];
-    load_row<NV>(r, x + row * V, V4, gl, -FLT_MAX);
+    load_row<NV>(r, x + (rowmap ? (int64_t)__ldg(rowmap + row) : row) * V, V4, gl, -FLT_MAX);
     float m, s;
     softmax_row<NV>(r, gm, m, s);
     store_row<NV>(y + row * V, r, V4, gl);
@@ -674,6 +676,17 @@ bool eodm_softmax_rows4_launch(const float* logits, int64_t rows, int V, float* 
     return cudaGetLastError() == cudaSuccess;
   }
 #define CALL(NV) softmax_rows_vec_kernel<NV><<<vec_grid(rows, sms), 256, 0, st>>>(logits, V, rows, px)
+  EODM_DISPATCH_NV(vec_nv(V), CALL);
+#undef CALL
+  return cudaGetLastError() == cudaSuccess;
+}
+
+// the same over packed rows (V % 4 == 0, V <= 128): px[p] = softmax(logits[rowmap[p]]), p < *nrp; false = not handled
+bool eodm_softmax_rows4_packed_launch(const float* logits, int64_t rows_cap, int V, const int* rowmap, const int* nrp,
+                                      float* px, cudaStream_t st) {
+  const int sms = aux_sm_count();
+  if ((V & 3) != 0 || V > 128 || sms <= 0 || ((((uintptr_t)logits | (uintptr_t)px) & 15) != 0)) return false;
+#define CALL(NV) softmax_rows_vec_kernel<NV><<<vec_grid(rows_cap, sms), 256, 0, st>>>(logits, V, rows_cap, px, rowmap, nrp)
   EODM_DISPATCH_NV(vec_nv(V), CALL);
 #undef CALL
   return cudaGetLastError() == cudaSuccess;

@@ -166,9 +166,14 @@ __global__ void __launch_bounds__(1024) eodm_pack_scan_kernel(int* __restrict__ 
     counts[1] = frames_s;
   }
 }
+// w_out / inv (optional): the views for kernels that work on PHYSICALLY packed rows (the tensor-core kernels read their
+// tiles by TMA): w_out[p] = 1 if a window of kernel_size n may start at packed row p, 0 beyond the packed rows;
+// inv[row] = packed index of a padded row, -1 if it takes part in no window; and the row map's tail points at row 0 so
+// that a gather over all NR slots stays inside the batch.
 __global__ void __launch_bounds__(256) eodm_pack_fill_kernel(const uint8_t* __restrict__ mask, long long NR, int T, int n,
                                                              const int* __restrict__ boff, int* __restrict__ rowmap,
-                                                             uint8_t* __restrict__ wflag) {
+                                                             uint8_t* __restrict__ wflag, const int* __restrict__ counts,
+                                                             uint8_t* __restrict__ w_out, int* __restrict__ inv) {
   __shared__ int wsum[8];
   const long long r0 = (long long)blockIdx.x * kPackRows + threadIdx.x * 4;
   bool keep[4];
@@ -188,13 +193,33 @@ __global__ void __launch_bounds__(256) eodm_pack_fill_kernel(const uint8_t* __re
   __syncthreads();
   int p = boff[blockIdx.x] + x - k;
   for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) p += wsum[w];
+  const unsigned bit = 1u << (n - 1);
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < 4; ++u) {
     if (keep[u]) {
+      const unsigned wb = pack_wbits(mask, r0 + u, T);
       rowmap[p] = (int)(r0 + u);
-      wflag[p] = (uint8_t)pack_wbits(mask, r0 + u, T);
+      wflag[p] = (uint8_t)wb;
+      if (w_out) {
+        w_out[p] = (wb & bit) ? 1 : 0;
+        inv[r0 + u] = p;
+      }
       ++p;
+    } else if (w_out && r0 + u < NR) {
+      inv[r0 + u] = -1;
     }
+  }
+  if (w_out) {   // the slots behind the packed rows
+    const long long nrp = counts[0];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = r0 + u;
+      if (q >= nrp && q < NR) {
+        w_out[q] = 0;
+        rowmap[q] = 0;
+      }
+    }
+  }
 }
 
 __host__ __device__ inline int odd_ld(int x) { return x | 1; }
@@ -980,7 +1005,8 @@ static void ws_carve(const eodm_table* t, void* ws, float** part, int** cnt, flo
 // 1024) i32][packed rows, frames: 2 i32]
 size_t eodm_pack_workspace_bytes(long long NR) {
   const size_t n_blk = (size_t)((NR + kPackRows - 1) / kPackRows);
-  return up256((size_t)NR * sizeof(int)) + up256((size_t)NR) + 2 * up256(n_blk * sizeof(int)) + 256 + 256;
+  return up256((size_t)NR * sizeof(int)) + up256((size_t)NR) + 2 * up256(n_blk * sizeof(int)) + 256 + 256 +
+         up256((size_t)NR) + up256((size_t)NR * sizeof(int));   // + the views of eodm_pack_views_launch: w_out, inv
 }
 
 int g_packing = 1;   // test hook (eodm_debug_set_packing): 0 = walk the padded rows as round 1 did
@@ -989,7 +1015,7 @@ int g_packing = 1;   // test hook (eodm_debug_set_packing): 0 = walk the padded 
 // THIS batch made for kernel_size packed_n >= n (eodm_pack_rows_launch, or an earlier walk of the same step): its row
 // list is a superset of what this table needs and its flags carry a bit per kernel_size, so it is used as it is.
 static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack_ws, cudaStream_t st, PackView* pk,
-                     int packed_n = 0) {
+                     int packed_n = 0, uint8_t* w_out = nullptr, int* inv = nullptr) {
   pk->rowmap = nullptr;
   pk->wflag = nullptr;
   pk->counts = nullptr;
@@ -1010,7 +1036,7 @@ static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack
   if (packed_n == 0) {
     eodm_pack_count_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, bfr);
     eodm_pack_scan_kernel<<<1, 1024, 0, st>>>(bsum, bfr, n_blk, counts);
-    eodm_pack_fill_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, rowmap, wflag);
+    eodm_pack_fill_kernel<<<n_blk, 256, 0, st>>>(mask, NR, T, n, bsum, rowmap, wflag, counts, w_out, inv);
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1020,6 +1046,34 @@ static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack
   pk->rowmap = rowmap;
   pk->wflag = wflag;
   pk->counts = counts;
+  return EODM_OK;
+}
+
+// Packs the batch for kernel_size n and writes the views of eodm_pack_fill_kernel along (see there).  The region must be
+// eodm_pack_workspace_bytes(B * T) bytes.
+int eodm_pack_views_launch(const uint8_t* mask, int B, int T, int n, void* pack_ws, cudaStream_t st, EodmPackViews* out) {
+  const long long NR = (long long)B * T;
+  if (!pack_ws || NR > 0x7fffffffLL || n < 1 || n > 8) {
+    eodm_set_error("row packing: bad arguments");
+    return EODM_EINVAL;
+  }
+  char* p = (char*)(((uintptr_t)pack_ws + 255) & ~(uintptr_t)255);
+  const size_t n_blk = (size_t)((NR + kPackRows - 1) / kPackRows);
+  p += up256((size_t)NR * sizeof(int)) + up256((size_t)NR) + 2 * up256(n_blk * sizeof(int)) + 256;
+  uint8_t* w_out = (uint8_t*)p;
+  int* inv = (int*)(p + up256((size_t)NR));
+  PackView pk;
+  const int saved = g_packing, saved_ts = g_force_ts;
+  g_packing = 1;      // this caller asked for a packing explicitly
+  g_force_ts = 0;
+  const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk, 0, w_out, inv);
+  g_packing = saved;
+  g_force_ts = saved_ts;
+  if (rc != EODM_OK) return rc;
+  out->rowmap = pk.rowmap;
+  out->wstart = w_out;
+  out->inv = inv;
+  out->counts = pk.counts;
   return EODM_OK;
 }
 

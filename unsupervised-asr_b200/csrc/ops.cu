@@ -114,14 +114,16 @@ __global__ void __launch_bounds__(256) eodm_softmax_fwd_vec_kernel(const float* 
 template <int G>
 __global__ void __launch_bounds__(256) eodm_softmax_bwd_vec_kernel(const float* __restrict__ px,
                                                                    const float* __restrict__ dpx, int64_t rows, int V,
-                                                                   float* __restrict__ dx) {
+                                                                   float* __restrict__ dx, const int* __restrict__ inv = nullptr) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int gl = threadIdx.x % G;
   const bool live = row < rows && gl * 4 < V;
+  // packed rows (sessions): padded row `row` reads packed row inv[row]; a row that takes part in no window gets zeros
+  const int64_t src = (inv && row < rows) ? (int64_t)__ldg(inv + row) : row;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), d = p;
-  if (live) {
-    p = __ldg(reinterpret_cast<const float4*>(px + row * V) + gl);
-    d = __ldg(reinterpret_cast<const float4*>(dpx + row * V) + gl);
+  if (live && src >= 0) {
+    p = __ldg(reinterpret_cast<const float4*>(px + src * V) + gl);
+    d = __ldg(reinterpret_cast<const float4*>(dpx + src * V) + gl);
   }
   float s = fmaf(p.x, d.x, fmaf(p.y, d.y, fmaf(p.z, d.z, p.w * d.w)));
 #pragma unroll
@@ -161,6 +163,49 @@ __global__ void __launch_bounds__(256) eodm_softmax_bwd_kernel(const float* __re
   for (int v = lane; v < V; v += 32) s = fmaf(p[v], d[v], s);
   s = warp_sum(s);
   for (int v = lane; v < V; v += 32) dx[row * V + v] = p[v] * (d[v] - s);
+}
+
+// Softmax over PACKED rows (sessions that pack a ragged batch for the tensor-core kernels): packed row p is the softmax of
+// padded row rowmap[p]; only the *nrp packed rows are computed.  One warp per row.
+__global__ void __launch_bounds__(256) eodm_softmax_fwd_packed_kernel(const float* __restrict__ x, const int* __restrict__ rowmap,
+                                                                      const int* __restrict__ nrp, int V,
+                                                                      float* __restrict__ y) {
+  const int64_t rows = *nrp;
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const float* xr = x + (int64_t)__ldg(rowmap + row) * V;
+    float* yr = y + row * V;
+    float m = -FLT_MAX;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, xr[v]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(xr[v] - m);
+    s = warp_sum(s);
+    for (int v = lane; v < V; v += 32) yr[v] = expf(xr[v] - m) / s;
+  }
+}
+// ... and its VJP written back in the padded layout: dlogits[r] = px[p] * (dpx[p] - sum_v px[p] dpx[p]) with p = inv[r],
+// zero for the rows that take part in no window (inv[r] < 0)
+__global__ void __launch_bounds__(256) eodm_softmax_bwd_packed_kernel(const float* __restrict__ px, const float* __restrict__ dpx,
+                                                                      const int* __restrict__ inv, int64_t rows, int V,
+                                                                      float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int p_row = __ldg(inv + row);
+    float* out = dx + row * V;
+    if (p_row < 0) {
+      for (int v = lane; v < V; v += 32) out[v] = 0.f;
+      continue;
+    }
+    const float* p = px + (int64_t)p_row * V;
+    const float* d = dpx + (int64_t)p_row * V;
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s = fmaf(p[v], d[v], s);
+    s = warp_sum(s);
+    for (int v = lane; v < V; v += 32) out[v] = p[v] * (d[v] - s);
+  }
 }
 
 // p[b][t][z] = prod_{j < order[z]} (px[b][t+j][ids[z][j]] + eps)
@@ -333,6 +378,34 @@ int eodm_softmax_bwd_launch(const float* px, const float* dpx, int64_t rows, int
   const int wpb = 8;
   eodm_softmax_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(px, dpx, rows, V, dlogits);
   EODM_CHECK_LAUNCH("eodm_softmax_bwd_kernel");
+  return EODM_OK;
+}
+
+int eodm_softmax_fwd_packed_launch(const float* logits, int64_t rows_cap, int V, const int* rowmap, const int* nrp, float* px,
+                                   cudaStream_t st) {
+  if (rows_cap == 0) return EODM_OK;
+  if (eodm_softmax_rows4_packed_launch(logits, rows_cap, V, rowmap, nrp, px, st)) return EODM_OK;
+  int64_t grid = (rows_cap + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  eodm_softmax_fwd_packed_kernel<<<(unsigned)grid, 256, 0, st>>>(logits, rowmap, nrp, V, px);
+  EODM_CHECK_LAUNCH("eodm_softmax_fwd_packed_kernel");
+  return EODM_OK;
+}
+int eodm_softmax_bwd_packed_launch(const float* px, const float* dpx, int64_t rows, int V, const int* inv, float* dlogits,
+                                   cudaStream_t st) {
+  if (rows == 0) return EODM_OK;
+  {
+    const int G = vec_group(V);
+    if (G && (((uintptr_t)px | (uintptr_t)dpx | (uintptr_t)dlogits) & 15) == 0 && rows * G / 256 < 0x7fffffffLL) {
+      EODM_SOFTMAX_DISPATCH(eodm_softmax_bwd_vec_kernel, G, px, dpx, rows, V, dlogits, inv);
+      EODM_CHECK_LAUNCH("eodm_softmax_bwd_vec_kernel");
+      return EODM_OK;
+    }
+  }
+  int64_t grid = (rows + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  eodm_softmax_bwd_packed_kernel<<<(unsigned)grid, 256, 0, st>>>(px, dpx, inv, rows, V, dlogits);
+  EODM_CHECK_LAUNCH("eodm_softmax_bwd_packed_kernel");
   return EODM_OK;
 }
 

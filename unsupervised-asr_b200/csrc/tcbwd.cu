@@ -73,6 +73,7 @@ struct BArgs {
   int T, V, n_tiles;
   int px_tma;        // 1: the posterior tile is staged by TMA (V % 4 == 0), 0: by loads
   int accumulate;    // 1: dpx += (several tables over one posterior sequence), 0: dpx =
+  const int* nrp;    // packed rows (session packing): the tile count comes from *nrp, on the device
   long long* prof;   // debug: per-CTA cycle counters (eodm_debug_tcb_profile), nullptr in production
   int dbg;           // debug (timing experiments only, results are wrong): 1 = no TMA, 2 = no epilogue work
 };
@@ -258,7 +259,8 @@ eodm_tc_bwd_kernel(const __grid_constant__ CUtensorMap tg, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_tp = (a.n_tiles + 1) >> 1;
+  const int n_tiles_dev = a.nrp ? (int)(((long long)*a.nrp + kTileRows - 1) / kTileRows) : a.n_tiles;
+  const int n_tp = (n_tiles_dev + 1) >> 1;
   const int my_tp = (n_tp - pair + n_pairs - 1) / n_pairs;
   long long* prof = (PROF && a.prof) ? a.prof + (size_t)blockIdx.x * 16 : nullptr;
 
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(256) eodm_tcb_image_kernel(const float* __rest
 struct TailArgs {
   const float* partS;      // forward partials, or nullptr: read S
   const int* partN;
+  const int* n_frames;     // optional: N from here (the row packing's frame count) instead of the slices' counts
   int n_slices, vp;
   long long slice_stride;
   float* S;                // [K] written (partials) or read
@@ -686,7 +689,8 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant
     float n;
     if (a.partS) {
       int c = 0;
-      for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
+      if (a.n_frames) c = *a.n_frames;
+      else for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
       n = (float)c;
       if (blockIdx.x == 0) a.N[0] = n;
     } else {
@@ -748,7 +752,8 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_con
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int c = 0;
-    for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
+    if (a.n_frames) c = *a.n_frames;
+    else for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
     slot[pv.K] = (float)c;
   }
   __threadfence_system();
@@ -885,7 +890,7 @@ size_t eodm_tcb_workspace_bytes(const eodm_table* t) {
 }
 
 int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S_io, float* N_io, const float* py, float eps,
-                        float* loss, float* gS, void* ws_tcb, cudaStream_t st) {
+                        float* loss, float* gS, void* ws_tcb, cudaStream_t st, const int* n_frames) {
   if (!eodm_tcb_supported(t) || !t->d_ids) {
     eodm_set_error("fused tail needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -893,6 +898,7 @@ int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S
   TailArgs a;
   a.partS = parts ? parts->partS : nullptr;
   a.partN = parts ? parts->partN : nullptr;
+  a.n_frames = n_frames;
   a.n_slices = parts ? parts->n_slices : 0;
   a.vp = parts ? parts->vp : 0;
   a.slice_stride = parts ? parts->slice_stride : 0;
@@ -922,7 +928,7 @@ int eodm_tc_tail_launch(const eodm_table* t, const EodmTcfParts* parts, float* S
 
 int eodm_tc_tail_peer_launch(const eodm_table* t, const EodmTcfParts* parts, const EodmPeerView* pv, float* S_out,
                              float* N_out, const float* py, float eps, float* loss, float* gS, void* ws_tcb,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int* n_frames) {
   if (!eodm_tcb_supported(t) || !t->d_ids || !parts || !pv || pv->K != t->K) {
     eodm_set_error("fused tail with exchange: needs a trigram-only table over V <= 48, the forward's slice sums and a peer "
                    "group bootstrapped for this table's K");
@@ -931,6 +937,7 @@ int eodm_tc_tail_peer_launch(const eodm_table* t, const EodmTcfParts* parts, con
   TailArgs a;
   a.partS = parts->partS;
   a.partN = parts->partN;
+  a.n_frames = n_frames;
   a.n_slices = parts->n_slices;
   a.vp = parts->vp;
   a.slice_stride = parts->slice_stride;
@@ -961,7 +968,7 @@ int eodm_tc_tail_peer_launch(const eodm_table* t, const EodmTcfParts* parts, con
 }
 
 int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, const float* gS, float* dpx,
-                    void* ws, cudaStream_t st, int accumulate, int image_ready) {
+                    void* ws, cudaStream_t st, int accumulate, int image_ready, const int* nrp) {
   if (!eodm_tcb_supported(t)) {
     eodm_set_error("tensor-core VJP needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -1016,7 +1023,8 @@ int eodm_tcb_launch(const eodm_table* t, const float* px, const uint8_t* mask, i
   a.mask = mask;
   a.dpx = dpx;
   a.NR = NR;
-  a.T = T;
+  a.T = nrp ? 0x7fffffff : T;   // packed rows: one sequence, a window-start flag per row (mask)
+  a.nrp = nrp;
   a.V = t->V;
   a.prof = g_tcb_prof;
   a.dbg = g_tcb_dbg;

@@ -76,6 +76,8 @@ struct FArgs {
   long long NR, rows_per_slice;
   int T, V, n_slices;
   int bulk;                // 1: posterior tiles arrive by cp.async.bulk (V % 4 == 0, px 16-byte aligned), 0: by loads
+  const int* nrp;          // packed rows (session packing): how many of the NR rows count is known on the device only --
+                           // the slices are then cut here, from *nrp, over the n_slices the grid was launched for
 };
 
 struct FBars {
@@ -145,8 +147,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) eodm_tc_fwd3_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const long long w_begin = (long long)slice * a.rows_per_slice;
-  const long long w_end = (w_begin + a.rows_per_slice < a.NR) ? w_begin + a.rows_per_slice : a.NR;
+  long long rps = a.rows_per_slice, rows_all = a.NR;
+  if (a.nrp) {
+    rows_all = *a.nrp;
+    rps = ((rows_all + a.n_slices - 1) / a.n_slices + kSt - 1) / kSt * kSt;
+    if (rps < kSt) rps = kSt;
+  }
+  const long long w_begin = (long long)slice * rps;
+  const long long w_end = (w_begin + rps < rows_all) ? w_begin + rps : rows_all;
   const int total_st = w_end > w_begin ? (int)((w_end - w_begin + kSt - 1) / kSt) : 0;
   const int n_tiles = (total_st + kStPerTile - 1) / kStPerTile;
   // TMEM: accumulator of tile g at column 96 g; A stage (s, g) at 192 + (kMT s + g) * 32: [hi 16][lo 16].  One accumulator
@@ -503,7 +511,7 @@ size_t eodm_tcf_workspace_bytes(const eodm_table* t) {
 // The main kernel alone: per-slice partial sums partS[slice][a 48 + b][c] and per-slice frame counts.  What turns them into
 // S and N is either eodm_tc_fwd3_finish_kernel (below) or the fused tail of tcbwd.cu.
 int eodm_tcf_launch_main(const eodm_table* t, const float* px, const uint8_t* mask, int B, int T, void* ws, cudaStream_t st,
-                         EodmTcfParts* parts) {
+                         EodmTcfParts* parts, const int* nrp) {
   if (!eodm_tcf_supported(t)) {
     eodm_set_error("tensor-core forward needs a trigram-only table over V <= 48");
     return EODM_EUNSUPPORTED;
@@ -515,13 +523,14 @@ int eodm_tcf_launch_main(const eodm_table* t, const float* px, const uint8_t* ma
   a.partS = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   a.partN = (int*)(a.partS + (size_t)slices_for(t) * (kMTiles * 128) * kVP);
   a.NR = NR;
-  a.T = T;
+  a.T = nrp ? 0x7fffffff : T;   // packed rows are one sequence with a window-start flag per row (mask)
+  a.nrp = nrp;
   a.V = t->V;
   int n_slices = slices_for(t);
   long long rps = (NR + n_slices - 1) / n_slices;
   rps = (rps + kSt - 1) / kSt * kSt;
   if (rps < kSt) rps = kSt;
-  n_slices = (int)((NR + rps - 1) / rps);
+  if (!nrp) n_slices = (int)((NR + rps - 1) / rps);
   a.n_slices = n_slices;
   a.rows_per_slice = rps;
   a.bulk = ((t->V & 3) == 0 && (((uintptr_t)px) & 15) == 0) ? 1 : 0;

@@ -56,6 +56,7 @@ SIGNATURES = {
     "eodm_peer_failed": (_i, [_p]),
     "eodm_peer_set_timeout": (_i, [_p, C.c_double]),
     "eodm_session_set_peer": (_i, [_p, _p]),
+    "eodm_session_set_packing": (_i, [_p, _i]),
     "eodm_session_submit": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p]),
     "eodm_session_wait": (_i, [_p, _i]),
     "eodm_counts_partial": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),

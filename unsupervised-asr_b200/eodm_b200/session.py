@@ -86,6 +86,11 @@ class Session:
         """Use a dist.PeerGroup for the exchange of the following steps (None to undo)."""
         check(lib.eodm_session_set_peer(self._h, group.handle if group is not None else None))
 
+    def set_packing(self, on):
+        """Ragged batches on the tensor-core kernels: run the device step on the rows that take part in a window only
+        (eodm_session_set_packing).  Off by default."""
+        check(lib.eodm_session_set_packing(self._h, 1 if on else 0))
+
     def step_device(self, logits_ptr, mask_ptr, B, T, loss_ptr, dlogits_ptr, stream, comm=None):
         """Raw device-pointer step (ints): enqueue only."""
         check(lib.eodm_session_step_device(self._h, C.c_void_p(logits_ptr), C.c_void_p(mask_ptr), B, T,
