@@ -1015,12 +1015,13 @@ int g_packing = 1;   // test hook (eodm_debug_set_packing): 0 = walk the padded 
 // THIS batch made for kernel_size packed_n >= n (eodm_pack_rows_launch, or an earlier walk of the same step): its row
 // list is a superset of what this table needs and its flags carry a bit per kernel_size, so it is used as it is.
 static int pack_rows(const uint8_t* mask, long long NR, int T, int n, void* pack_ws, cudaStream_t st, PackView* pk,
-                     int packed_n = 0, uint8_t* w_out = nullptr, int* inv = nullptr) {
+                     int packed_n = 0, uint8_t* w_out = nullptr, int* inv = nullptr, bool force = false) {
   pk->rowmap = nullptr;
   pk->wflag = nullptr;
   pk->counts = nullptr;
   pk->bit = 1u << (n - 1);
-  if (!pack_ws || !g_packing || g_force_ts > 0 || NR > 0x7fffffffLL || n > 8) return EODM_OK;   // (a pinned tile height: padded rows)
+  // (the test hooks -- packing switched off, a pinned tile height -- mean padded rows, unless the caller needs the packing)
+  if (!pack_ws || NR > 0x7fffffffLL || n > 8 || (!force && (!g_packing || g_force_ts > 0))) return EODM_OK;
   if (packed_n > 0 && packed_n < n) packed_n = 0;
   char* p = (char*)(((uintptr_t)pack_ws + 255) & ~(uintptr_t)255);
   const int n_blk = (int)((NR + kPackRows - 1) / kPackRows);
@@ -1063,12 +1064,7 @@ int eodm_pack_views_launch(const uint8_t* mask, int B, int T, int n, void* pack_
   uint8_t* w_out = (uint8_t*)p;
   int* inv = (int*)(p + up256((size_t)NR));
   PackView pk;
-  const int saved = g_packing, saved_ts = g_force_ts;
-  g_packing = 1;      // this caller asked for a packing explicitly
-  g_force_ts = 0;
-  const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk, 0, w_out, inv);
-  g_packing = saved;
-  g_force_ts = saved_ts;
+  const int rc = pack_rows(mask, NR, T, n, pack_ws, st, &pk, 0, w_out, inv, true);   // this caller needs the packing
   if (rc != EODM_OK) return rc;
   out->rowmap = pk.rowmap;
   out->wstart = w_out;
