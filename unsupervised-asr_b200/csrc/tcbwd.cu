@@ -791,10 +791,13 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_con
   } else {
     if (threadIdx.x == 0) {
       unsigned v;
-      do {
+      const long long t0 = clock64();
+      int late = 0;
+      do {   // (bounded like the remote wait: should block 0 not be resident -- the grid is sized so that it is -- give up)
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
-      } while (v != step);
-      bad_s = *reinterpret_cast<volatile int*>(mine + 204);
+        if (v != step && pv.timeout_clk > 0 && clock64() - t0 > 2 * pv.timeout_clk) late = 1;
+      } while (v != step && !late);
+      bad_s = late ? 1 : *reinterpret_cast<volatile int*>(mine + 204);
     }
   }
   __syncthreads();
@@ -824,10 +827,13 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_con
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go2), "r"(step) : "memory");
     }
     unsigned v;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go2) : "memory");
+      if (v != step && pv.timeout_clk > 0 && clock64() - t0 > 2 * pv.timeout_clk) break;   // (see above; the sums are then NaN-checked by nobody: flag it)
     } while (v != step);
-    const float n = __ldcg(sum + pv.K);
+    if (v != step) bad_s = 1;
+    const float n = (v != step) ? __int_as_float(0x7fc00000) : __ldcg(sum + pv.K);
     n_s = n;
     if (blockIdx.x == 0) a.N[0] = n;
   }
