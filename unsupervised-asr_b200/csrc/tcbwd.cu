@@ -716,17 +716,31 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_kernel(const __grid_constant
 }
 
 // ---- the same with the exchange of a batch-sharded step inside (one process per GPU, buffers shared through CUDA IPC:
-//      peer.cu).  Phase A: every thread writes its trigrams' slice sums (this rank's partial counts) into the rank's
-//      peer-visible slot; the block that takes the last ticket raises the rank's flag to the step number.  Every block then
-//      waits for all ranks' flags (acquire loads over NVLink; the grid is sized to be co-resident, so a waiting block
-//      never keeps an unpublished one off the SMs).  Phase B: the ranks' counts are read straight out of peer memory and
-//      added in rank order -- identical bits on every rank -- and feed the loss terms, dloss/dS and the G image exactly as
-//      above.  Slots alternate by step parity (peer.cu explains why that is enough); the step counter is advanced by the
-//      last block, so a captured graph replays.  A peer that never arrives: NaN everywhere, error flag set.
+//      peer.cu).  The first ceil((K + 1) / 256) blocks are the exchange blocks, thread = table entry:
+//      A   each writes its entry's slice sum (this rank's partial count) into the rank's peer-visible slot; the exchange
+//          block that takes the last ticket raises the rank's flag to the step number;
+//      -   block 0 alone watches the peers' flags over NVLink and raises a local go word (with every block polling remote
+//          memory the polls queued up on the links and a raised flag was seen tens of microseconds late);
+//      B1  the ranks' counts are read out of peer memory with coalesced loads, added in rank order -- identical bits on
+//          every rank -- into a local plane; the last exchange block raises a second local word.
+//      All the blocks wait for that word (the grid is sized to be co-resident) and then do what the one-GPU tail does,
+//      B2: loss terms, dloss/dS and the G image from the plane, loss by the block with the last ticket.
+//      An earlier version ran A over the image elements in every block, with three grid-wide barriers: 22 us more than
+//      the one-GPU tail even in a group of one rank (tools/peer1_overhead.py).  Slots alternate by step parity (peer.cu
+//      explains why that is enough); the step counter is advanced by the last block, so a captured graph replays.  A
+//      peer that never arrives: NaN everywhere, error flag set.
 __device__ __forceinline__ unsigned tail_ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned tail_ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tail_st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_constant__ TailArgs a,
                                                                 const __grid_constant__ EodmPeerView pv) {
@@ -738,108 +752,102 @@ __global__ void __launch_bounds__(256) eodm_tc_tail_peer_kernel(const __grid_con
   unsigned* ctr = reinterpret_cast<unsigned*>(mine + 64);
   unsigned* ticket_a = reinterpret_cast<unsigned*>(mine + 192);
   unsigned* ticket_b = reinterpret_cast<unsigned*>(mine + 196);
+  unsigned* go = reinterpret_cast<unsigned*>(mine + 200);    // step number once every rank has published; [204]: timed out
+  unsigned* ticket_c = reinterpret_cast<unsigned*>(mine + 208);
+  unsigned* go2 = reinterpret_cast<unsigned*>(mine + 212);   // step number once the plane of global counts is complete
   const unsigned step = *reinterpret_cast<volatile unsigned*>(ctr) + 1u;   // advanced by the last block of this launch
   const size_t slot_off = EODM_PEER_HDR_BYTES + (size_t)(step & 1u) * pv.slot_bytes;
   float* slot = reinterpret_cast<float*>(mine + slot_off);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  // ---- phase A
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zmap_len; i += stride) {
-    int z = a.zmap[i];
-    if (z >= 0) {
-      const float s = tail_slice_sum(a, z);
-      for (; z >= 0; z = a.next_dup[z]) slot[z] = s;   // (every trigram sits in both GEMMs' images: written twice, same value)
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int c = 0;
-    if (a.n_frames) c = *a.n_frames;
-    else for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
-    slot[pv.K] = (float)c;
-  }
-  __threadfence_system();
+  float* sum = reinterpret_cast<float*>(mine + EODM_PEER_HDR_BYTES + 2 * pv.slot_bytes);
+  const unsigned n_x = min(gridDim.x, (unsigned)((pv.K + 1 + 255) / 256));   // exchange blocks
+  if (threadIdx.x == 0) bad_s = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    bad_s = 0;
-    if (atomicAdd(ticket_a, 1u) == gridDim.x - 1u) {   // every block of this rank has published
+  if (blockIdx.x < n_x) {
+    // ---- A: this rank's partial counts (entry K: its frames)
+    for (int z = blockIdx.x * 256 + threadIdx.x; z <= pv.K; z += (int)n_x * 256) {
+      if (z < pv.K) {
+        slot[z] = tail_slice_sum(a, z);
+      } else {
+        int c = 0;
+        if (a.n_frames) c = *a.n_frames;
+        else for (int sl = 0; sl < a.n_slices; ++sl) c += a.partN[sl];
+        slot[z] = (float)c;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket_a, 1u) == n_x - 1u) {   // every exchange block of this rank has published
       *ticket_a = 0;
       __threadfence_system();
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned*>(mine)), "r"(step) : "memory");
     }
-  }
-  __syncthreads();
-  // Block 0 alone watches the peers' flags over NVLink and then raises a LOCAL go word the other blocks watch in their own
-  // L2: with every block polling remote memory (3 000 pollers per rank) the polls queued up on the links and a raised flag
-  // was seen tens of microseconds late (0.433 ms per step at 8 GPUs against 0.401 with NCCL, profiles/r02_scaling.md).
-  unsigned* go = reinterpret_cast<unsigned*>(mine + 200);   // step number once every rank has published; [204]: timed out
-  if (blockIdx.x == 0) {
-    if (threadIdx.x < pv.world) {
-      const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
+    // ---- the peers
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < pv.world) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(pv.base[threadIdx.x]);
+        const long long t0 = clock64();
+        while ((int)(tail_ld_acquire_sys(flag) - step) < 0) {   // signed difference: the counter may wrap
+          if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {
+            bad_s = 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile int*>(mine + 204) = bad_s;
+        __threadfence();
+        tail_st_release_gpu(go, step);
+      }
+    } else if (threadIdx.x == 0) {
       const long long t0 = clock64();
-      while ((int)(tail_ld_acquire_sys(flag) - step) < 0) {   // signed difference: the counter may wrap
-        if (pv.timeout_clk > 0 && clock64() - t0 > pv.timeout_clk) {
+      while (tail_ld_acquire_gpu(go) != step)   // (bounded like the remote wait: block 0 is resident -- but give up if not)
+        if (pv.timeout_clk > 0 && clock64() - t0 > 2 * pv.timeout_clk) {
           bad_s = 1;
           break;
         }
-      }
+      if (!bad_s) bad_s = *reinterpret_cast<volatile int*>(mine + 204);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      *reinterpret_cast<volatile int*>(mine + 204) = bad_s;
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(step) : "memory");
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      unsigned v;
-      const long long t0 = clock64();
-      int late = 0;
-      do {   // (bounded like the remote wait: should block 0 not be resident -- the grid is sized so that it is -- give up)
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
-        if (v != step && pv.timeout_clk > 0 && clock64() - t0 > 2 * pv.timeout_clk) late = 1;
-      } while (v != step && !late);
-      bad_s = late ? 1 : *reinterpret_cast<volatile int*>(mine + 204);
-    }
-  }
-  __syncthreads();
-  const bool bad = bad_s != 0;
-  // ---- phase B1: the ranks' counts, added in rank order, into a local plane -- consecutive threads read consecutive
-  //      entries, so a rank serves 128-byte requests (a 40 KB slot per reader).  Reading the peers entry by entry from
-  //      phase B2's image order instead (scattered 4-byte loads, 155 k sectors served per rank) cost ~25 us at 8 GPUs.
-  float* sum = reinterpret_cast<float*>(mine + EODM_PEER_HDR_BYTES + 2 * pv.slot_bytes);
-  for (long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x; z <= pv.K; z += stride) {
-    float v[EODM_MAX_PEERS];
+    // ---- B1: global counts in rank order, coalesced reads of the peers' slots
+    const bool bad = bad_s != 0;
+    for (int z = blockIdx.x * 256 + threadIdx.x; z <= pv.K; z += (int)n_x * 256) {
+      float v[EODM_MAX_PEERS];
 #pragma unroll
-    for (int r = 0; r < EODM_MAX_PEERS; ++r)
-      v[r] = r < pv.world ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
-    float t = 0.f;
+      for (int r = 0; r < EODM_MAX_PEERS; ++r)
+        v[r] = r < pv.world ? __ldcv(reinterpret_cast<const float*>(pv.base[r] + slot_off) + z) : 0.f;
+      float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < EODM_MAX_PEERS; ++r) t += v[r];   // rank order; absent ranks add +0
-    sum[z] = bad ? __int_as_float(0x7fc00000) : t;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {   // grid barrier: the plane is complete before anyone reads it
-    unsigned* ticket_c = reinterpret_cast<unsigned*>(mine + 208);
-    unsigned* go2 = reinterpret_cast<unsigned*>(mine + 212);
-    if (atomicAdd(ticket_c, 1u) == gridDim.x - 1u) {
+      for (int r = 0; r < EODM_MAX_PEERS; ++r) t += v[r];   // rank order; absent ranks add +0
+      sum[z] = bad ? __int_as_float(0x7fc00000) : t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket_c, 1u) == n_x - 1u) {
       *ticket_c = 0;
+      if (bad) *reinterpret_cast<volatile int*>(mine + 204) = 1;
       __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go2), "r"(step) : "memory");
+      tail_st_release_gpu(go2, step);
     }
-    unsigned v;
+  }
+  // ---- every block: the plane is complete
+  if (threadIdx.x == 0) {
     const long long t0 = clock64();
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go2) : "memory");
-      if (v != step && pv.timeout_clk > 0 && clock64() - t0 > 2 * pv.timeout_clk) break;   // (see above; the sums are then NaN-checked by nobody: flag it)
-    } while (v != step);
-    if (v != step) bad_s = 1;
-    const float n = (v != step) ? __int_as_float(0x7fc00000) : __ldcg(sum + pv.K);
+    bool late = false;
+    while (tail_ld_acquire_gpu(go2) != step)
+      if (pv.timeout_clk > 0 && clock64() - t0 > 3 * pv.timeout_clk) {
+        late = true;
+        break;
+      }
+    if (late || *reinterpret_cast<volatile int*>(mine + 204)) bad_s = 1;
+    const float n = late ? __int_as_float(0x7fc00000) : __ldcg(sum + pv.K);
     n_s = n;
     if (blockIdx.x == 0) a.N[0] = n;
   }
   __syncthreads();
-  // ---- phase B2: loss terms, dloss/dS, G image
+  // ---- B2: loss terms, dloss/dS, G image
   const float n = n_s;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zmap_len; i += stride) {
     const int z = a.zmap[i];
     tail_element(a, i, z, z >= 0 ? __ldcg(sum + z) : 0.f, n, true);
