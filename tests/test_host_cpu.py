@@ -104,6 +104,34 @@ def test_oracle_literal_fp32_matches_reference_graph(golden, tag):
     assert np.abs(r["dlogits"] - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+def test_oracle_arbitrary_masks_literal_vs_direct_vs_c():
+    """Masks that are not prefixes (holes, a valid frame in the last n-1 slots, empty and full utterances): the literal
+    reference graph (O1: models/EODM.py:5-25 line for line -- the mask is tiled, cut to T' and multiplied in, so only the
+    window START is tested and N counts every valid frame) against the direct oracle (O2) and the C oracle.  The GPU
+    parity tests of the row packing lean on O2 / the C oracle for exactly such masks."""
+    from oracle import fast as F
+    rng = np.random.default_rng(7)
+    V, n, K, B, T = 12, 3, 60, 6, 17
+    ids, py = O.synth_table(V, n, K, seed=3)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    mask = rng.random((B, T)) < 0.55
+    mask[0] = False
+    mask[1] = True
+    mask[2, :] = False; mask[2, T - 1] = True
+    mask[3, :] = False; mask[3, T - n] = True
+    lit = O.eodm_loss_literal(logits, mask, O.ids_to_kernel(ids, V), py, dtype="float64")
+    d = O.eodm_loss_direct(logits, mask, ids, n, py)
+    c = F.eodm_loss_direct(logits, mask, ids, n, py)
+    for r in (d, c):
+        assert abs(r["loss"] - float(lit["loss"])) <= 1e-12 * abs(float(lit["loss"]))
+        assert np.abs(r["dlogits"] - lit["dlogits"]).max() <= 1e-12 * np.abs(lit["dlogits"]).max()
+    # rows no window touches get exactly zero gradient
+    touched = np.zeros((B, T), dtype=bool)
+    for k in range(n):
+        touched[:, k:] |= (mask & (np.arange(T)[None, :] <= T - n))[:, :T - k]
+    assert np.all(d["dlogits"][~touched] == 0)
+
+
 def test_oracle_known_answer_uniform():
     # SURVEY.md 8c(2): uniform posterior, full mask -> loss = n ln V - ln((T-n+1)/T)
     V, n, K, B, T = 40, 5, 50, 3, 17
