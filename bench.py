@@ -51,7 +51,8 @@ def config_of(w, name, world):
     return {"workload": name, "B_per_gpu": w["B"], "T": w["T"], "V": w["V"], "n": w["n"], "K": w["K"],
             "frames_per_step": int(w["mask"].sum()) * world,
             "boundary": "_logits -> loss, dloss/d_logits (softmax inside)",
-            "parallelism": "batch-sharded x%d" % world}
+            "parallelism": "batch-sharded x%d" % world,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write)"}
 
 
 def parse():
